@@ -1,0 +1,258 @@
+"""ctypes binding of libgoalforce_b200.so (the C ABI in include/goalforce_b200.h).
+
+torch is used only to own device memory and streams: every call hands raw device pointers and the current
+CUDA stream to the library. There is no CPU or PyTorch fallback: if the library is missing or a call fails the
+wrappers raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+
+import torch
+
+_LIB = None
+
+GF_EPI_BIAS = 0
+GF_EPI_BIAS_GELU = 1
+GF_EPI_BIAS_SILU = 2
+GF_EPI_GATE_RES = 3
+
+_ERRORS = {-1: "GF_ERR_BAD_ARG", -2: "GF_ERR_NO_DRIVER", -3: "GF_ERR_TMAP", -4: "GF_ERR_UNSUPPORTED"}
+
+# name -> argtypes; every entry point returns int
+_p, _ll, _i, _f = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float
+SIGNATURES = {
+    "gf_abi_version": [],
+    "gf_device_sms": [],
+    "gf_gemm_bf16": [_p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p, _i, _p, _p, _ll, _i, _p],
+    "gf_layernorm_bf16": [_p, _ll, _p, _ll, _i, _i, _f, _p, _p, _p, _p, _p],
+    "gf_rmsnorm_rope_bf16": [_p, _ll, _i, _i, _p, _f, _p, _i, _p],
+    "gf_attention_bf16": [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _f, _p],
+    "gf_patch_gather_bf16": [_p, _i, _p, _i, _p, _ll, _i, _i, _i, _p],
+    "gf_unpatchify_bf16": [_p, _ll, _p, _i, _i, _i, _i, _p],
+    "gf_add_rows_bf16": [_p, _p, _p, _i, _i, _p],
+    "gf_silu_bf16": [_p, _p, _ll, _p],
+    "gf_cfg_euler_bf16": [_p, _p, _p, _p, _f, _f, _ll, _p],
+    "gf_ulysses_pack_bf16": [_p, _ll, _p, _i, _i, _i, _i, _p],
+    "gf_ulysses_unpack_bf16": [_p, _p, _ll, _i, _i, _i, _i, _p],
+}
+
+
+def lib_path() -> Path:
+    return Path(__file__).resolve().parent / "_lib" / "libgoalforce_b200.so"
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (building it first when GF_B200_AUTOBUILD=1 and it is absent)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not path.exists():
+        if os.environ.get("GF_B200_AUTOBUILD", "0") == "1":
+            from . import build as _build
+            _build.build()
+        else:
+            raise RuntimeError(
+                f"{path} is missing: run `python -m goal_force_b200.build` (or __graft_entry__.build()). "
+                "goal_force_b200 has no CPU/PyTorch fallback.")
+    lib = ctypes.CDLL(str(path))
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # raises AttributeError if a declared symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    if lib.gf_abi_version() != 1:
+        raise RuntimeError("libgoalforce_b200.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        name = _ERRORS.get(rc, f"cudaError {rc}")
+        raise RuntimeError(f"{what} failed: {name}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.bfloat16) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (goal_force_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.dim() >= 1 and t.stride(-1) != 1:
+        raise ValueError(f"{name} must be contiguous in its last dimension")
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.dim() == 2 else t.shape[-1]
+
+
+# ------------------------------------------------------------------------------------------------ wrappers
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, epi: int = GF_EPI_BIAS,
+         gate: torch.Tensor | None = None, residual: torch.Tensor | None = None,
+         out: torch.Tensor | None = None, cta_group: int = 2) -> torch.Tensor:
+    """out[M,N] = epi(a[M,K] @ w[N,K]^T): F.linear with the fused tails of GF_EPI_*."""
+    _req(a, "a"); _req(w, "w")
+    if a.dim() != 2 or w.dim() != 2 or a.shape[1] != w.shape[1]:
+        raise ValueError(f"gemm shape mismatch: a {tuple(a.shape)} w {tuple(w.shape)}")
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _req(out, "out")
+    if out.shape != (M, N):
+        raise ValueError("out has wrong shape")
+    if bias is not None:
+        _req(bias, "bias")
+    if epi == GF_EPI_GATE_RES:
+        if residual is None:
+            raise ValueError("GF_EPI_GATE_RES needs a residual")
+        _req(residual, "residual")
+        if gate is not None:
+            _req(gate, "gate")
+    rc = load().gf_gemm_bf16(a.data_ptr(), _ld(a), w.data_ptr(), _ld(w), out.data_ptr(), _ld(out), M, N, K,
+                             _ptr(bias), epi, _ptr(gate), _ptr(residual),
+                             _ld(residual) if residual is not None else 0, cta_group, _stream())
+    _check(rc, "gf_gemm_bf16")
+    return out
+
+
+def layernorm(x: torch.Tensor, *, eps: float, shift: torch.Tensor | None = None, scale: torch.Tensor | None = None,
+              weight: torch.Tensor | None = None, bias: torch.Tensor | None = None,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    _req(x, "x")
+    rows, d = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    for n, t in (("shift", shift), ("scale", scale), ("weight", weight), ("bias", bias)):
+        if t is not None:
+            _req(t, n)
+    rc = load().gf_layernorm_bf16(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), rows, d, eps, _ptr(shift),
+                                  _ptr(scale), _ptr(weight), _ptr(bias), _stream())
+    _check(rc, "gf_layernorm_bf16")
+    return out
+
+
+def rmsnorm_rope_(x: torch.Tensor, weight: torch.Tensor, *, eps: float, cos_sin: torch.Tensor | None,
+                  head_dim: int, d: int | None = None) -> torch.Tensor:
+    """In place on the first `d` columns of x[rows, ld]."""
+    _req(x, "x"); _req(weight, "weight")
+    rows = x.shape[0]
+    d = weight.numel() if d is None else d
+    if cos_sin is not None:
+        _req(cos_sin, "cos_sin", torch.float32)
+        if cos_sin.shape != (rows, head_dim // 2, 2) or not cos_sin.is_contiguous():
+            raise ValueError(f"cos_sin must be contiguous [rows, head_dim/2, 2], got {tuple(cos_sin.shape)}")
+    rc = load().gf_rmsnorm_rope_bf16(x.data_ptr(), _ld(x), rows, d, weight.data_ptr(), eps, _ptr(cos_sin), head_dim,
+                                     _stream())
+    _check(rc, "gf_rmsnorm_rope_bf16")
+    return x
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, out: torch.Tensor | None = None,
+              scale: float | None = None) -> torch.Tensor:
+    """q: [Lq, >=heads*128] view, k/v: [Lk, ...] views (row pitch taken from stride(0))."""
+    _req(q, "q"); _req(k, "k"); _req(v, "v")
+    head_dim = 128
+    Lq, Lk = q.shape[0], k.shape[0]
+    if out is None:
+        out = torch.empty((Lq, heads * head_dim), dtype=torch.bfloat16, device=q.device)
+    if scale is None:
+        scale = head_dim ** -0.5
+    rc = load().gf_attention_bf16(q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(),
+                                  _ld(out), Lq, Lk, heads, head_dim, scale, _stream())
+    _check(rc, "gf_attention_bf16")
+    return out
+
+
+def patch_gather(src0: torch.Tensor, src1: torch.Tensor | None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """src*: (C, F, H, W) contiguous bf16 -> tokens [F*H/2*W/2, (C0+C1)*4]."""
+    _req(src0, "src0")
+    C0, F, H, W = src0.shape
+    C1 = 0
+    if src1 is not None:
+        _req(src1, "src1")
+        C1 = src1.shape[0]
+        if tuple(src1.shape[1:]) != (F, H, W):
+            raise ValueError("src1 spatial shape mismatch")
+    if not src0.is_contiguous() or (src1 is not None and not src1.is_contiguous()):
+        raise ValueError("patch_gather sources must be contiguous")
+    L = F * (H // 2) * (W // 2)
+    if out is None:
+        out = torch.empty((L, (C0 + C1) * 4), dtype=torch.bfloat16, device=src0.device)
+    rc = load().gf_patch_gather_bf16(src0.data_ptr(), C0, _ptr(src1), C1, out.data_ptr(), _ld(out), F, H, W,
+                                     _stream())
+    _check(rc, "gf_patch_gather_bf16")
+    return out
+
+
+def unpatchify(tokens: torch.Tensor, C: int, F: int, H: int, W: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    _req(tokens, "tokens")
+    if out is None:
+        out = torch.empty((C, F, H, W), dtype=torch.bfloat16, device=tokens.device)
+    rc = load().gf_unpatchify_bf16(tokens.data_ptr(), _ld(tokens), out.data_ptr(), C, F, H, W, _stream())
+    _check(rc, "gf_unpatchify_bf16")
+    return out
+
+
+def add_rows(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    _req(a, "a"); _req(b, "b")
+    a2 = a.reshape(-1, b.numel())
+    if out is None:
+        out = torch.empty_like(a2)
+    rc = load().gf_add_rows_bf16(a2.data_ptr(), b.data_ptr(), out.data_ptr(), a2.shape[0], a2.shape[1], _stream())
+    _check(rc, "gf_add_rows_bf16")
+    return out.view(a.shape)
+
+
+def silu(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    _req(x, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    rc = load().gf_silu_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    _check(rc, "gf_silu_bf16")
+    return out
+
+
+def cfg_euler(posi: torch.Tensor, nega: torch.Tensor | None, latents: torch.Tensor, cfg_scale: float, dsigma: float,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    _req(posi, "posi"); _req(latents, "latents")
+    if nega is not None:
+        _req(nega, "nega")
+    if out is None:
+        out = torch.empty_like(latents)
+    rc = load().gf_cfg_euler_bf16(posi.data_ptr(), _ptr(nega), latents.data_ptr(), out.data_ptr(), cfg_scale, dsigma,
+                                  latents.numel(), _stream())
+    _check(rc, "gf_cfg_euler_bf16")
+    return out
+
+
+def ulysses_pack(x: torch.Tensor, heads: int, head_dim: int, P: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """x[rows, >=heads*head_dim] -> out[P, rows, heads/P, head_dim] (contiguous per-destination blocks)."""
+    _req(x, "x")
+    rows = x.shape[0]
+    if out is None:
+        out = torch.empty((P, rows, heads // P, head_dim), dtype=torch.bfloat16, device=x.device)
+    rc = load().gf_ulysses_pack_bf16(x.data_ptr(), _ld(x), out.data_ptr(), rows, heads, head_dim, P, _stream())
+    _check(rc, "gf_ulysses_pack_bf16")
+    return out
+
+
+def ulysses_unpack(inp: torch.Tensor, rows: int, heads: int, head_dim: int, P: int,
+                   out: torch.Tensor | None = None) -> torch.Tensor:
+    """inp[P, rows, heads/P, head_dim] -> out[rows, heads*head_dim]."""
+    _req(inp, "inp")
+    if out is None:
+        out = torch.empty((rows, heads * head_dim), dtype=torch.bfloat16, device=inp.device)
+    rc = load().gf_ulysses_unpack_bf16(inp.data_ptr(), out.data_ptr(), _ld(out), rows, heads, head_dim, P, _stream())
+    _check(rc, "gf_ulysses_unpack_bf16")
+    return out

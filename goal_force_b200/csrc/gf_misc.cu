@@ -1,0 +1,187 @@
+// gf_misc.cu -- small HBM-bound kernels around the DiT blocks: patch gather / unpatchify (index shuffles, bit-exact),
+// modulation add, SiLU, CFG + Euler update, Ulysses pack/unpack.  All are pure streaming kernels; grids are sized to
+// a few waves of 148 SMs and every global access is 4-16 bytes per thread, coalesced on the output side.
+#include "gf_ptx.cuh"
+#include "gf_api_internal.h"
+
+namespace gf {
+
+// out[(f*H2+h)*W2 + w, c*4 + kh*2 + kw] = src[c, f, 2h+kh, 2w+kw]
+// One thread produces the 4 bf16 (kh,kw) of one (token, channel): two 4-byte loads (rows 2h, 2h+1), one 8-byte store.
+__global__ void patch_gather_kernel(const __nv_bfloat16* __restrict__ s0, int C0, const __nv_bfloat16* __restrict__ s1,
+                                    int C1, __nv_bfloat16* __restrict__ out, long long ldo, int F, int H, int W) {
+  const int H2 = H >> 1, W2 = W >> 1, C = C0 + C1;
+  const long long total = (long long)F * H2 * W2 * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long tok = i / C;
+    const int w = (int)(tok % W2);
+    const int h = (int)((tok / W2) % H2);
+    const int f = (int)(tok / ((long long)W2 * H2));
+    const __nv_bfloat16* src = (c < C0) ? s0 + (long long)c * F * H * W : s1 + (long long)(c - C0) * F * H * W;
+    const __nv_bfloat16* p = src + ((long long)f * H + 2 * h) * W + 2 * w;
+    const uint32_t r0 = *reinterpret_cast<const uint32_t*>(p);
+    const uint32_t r1 = *reinterpret_cast<const uint32_t*>(p + W);
+    *reinterpret_cast<uint2*>(out + tok * ldo + c * 4) = make_uint2(r0, r1);
+  }
+}
+
+// out[c, f, 2h+kh, 2w+kw] = tokens[(f*H2+h)*W2 + w, (kh*2+kw)*C + c]      (out is (C, F, H, W))
+__global__ void unpatchify_kernel(const __nv_bfloat16* __restrict__ t, long long ldt, __nv_bfloat16* __restrict__ out,
+                                  int C, int F, int H, int W) {
+  const int H2 = H >> 1, W2 = W >> 1;
+  const long long total = (long long)C * F * H * W2;  // one thread per output pair (kw = 0, 1)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W2);
+    const int y = (int)((i / W2) % H);
+    const int f = (int)((i / ((long long)W2 * H)) % F);
+    const int c = (int)(i / ((long long)W2 * H * F));
+    const int h = y >> 1, kh = y & 1;
+    const __nv_bfloat16* row = t + (((long long)f * H2 + h) * W2 + w) * ldt;
+    const __nv_bfloat16 a = row[(kh * 2 + 0) * C + c];
+    const __nv_bfloat16 b = row[(kh * 2 + 1) * C + c];
+    __nv_bfloat162 v; v.x = a; v.y = b;
+    *reinterpret_cast<__nv_bfloat162*>(out + (((long long)c * F + f) * H + y) * W + 2 * w) = v;
+  }
+}
+
+__global__ void add_rows_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                __nv_bfloat16* __restrict__ y, int rows, int cols) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn(__bfloat162float(a[i]) + __bfloat162float(b[i % cols]));
+}
+
+__global__ void silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = __bfloat162float(x[i]);
+    y[i] = __float2bfloat16_rn(v / (1.0f + expf(-v)));
+  }
+}
+
+// pred = nega + s*(posi - nega) ; out = lat + pred*dsigma, bf16 rounding after each torch op of the reference
+__global__ void cfg_euler_kernel(const __nv_bfloat16* __restrict__ posi, const __nv_bfloat16* __restrict__ nega,
+                                 const __nv_bfloat16* __restrict__ lat, __nv_bfloat16* __restrict__ out, float s,
+                                 float dsigma, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float p = __bfloat162float(posi[i]);
+    if (nega) {
+      const float q = __bfloat162float(nega[i]);
+      const float diff = round_bf16(p - q);
+      const float sc = round_bf16(s * diff);
+      p = round_bf16(q + sc);
+    }
+    const float upd = round_bf16(p * dsigma);
+    out[i] = __float2bfloat16_rn(__bfloat162float(lat[i]) + upd);
+  }
+}
+
+// x[rows, heads, hd] (row pitch ldx) -> out[P][rows][heads/P][hd]; 16-byte vectors
+__global__ void ulysses_pack_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out,
+                                    int rows, int heads, int hd, int P) {
+  const int vec_per_row = heads * hd / 8;
+  const int hp = heads / P;
+  const int vec_per_head = hd / 8;
+  const long long total = (long long)rows * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int vcol = (int)(i % vec_per_row);
+    const long long row = i / vec_per_row;
+    const int head = vcol / vec_per_head, j = vcol % vec_per_head;
+    const int dst = head / hp, hl = head % hp;
+    const uint4 v = *reinterpret_cast<const uint4*>(x + row * ldx + (long long)vcol * 8);
+    *reinterpret_cast<uint4*>(out + ((((long long)dst * rows + row) * hp + hl) * hd) + j * 8) = v;
+  }
+}
+// in[P][rows][heads/P][hd] -> y[rows, heads, hd] (row pitch ldy)
+__global__ void ulysses_unpack_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ y,
+                                      long long ldy, int rows, int heads, int hd, int P) {
+  const int vec_per_row = heads * hd / 8;
+  const int hp = heads / P;
+  const int vec_per_head = hd / 8;
+  const long long total = (long long)rows * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int vcol = (int)(i % vec_per_row);
+    const long long row = i / vec_per_row;
+    const int head = vcol / vec_per_head, j = vcol % vec_per_head;
+    const int src = head / hp, hl = head % hp;
+    const uint4 v = *reinterpret_cast<const uint4*>(in + ((((long long)src * rows + row) * hp + hl) * hd) + j * 8);
+    *reinterpret_cast<uint4*>(y + row * ldy + (long long)vcol * 8) = v;
+  }
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)gf_num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace gf
+
+using namespace gf;
+typedef __nv_bfloat16 bf16;
+#define GF_STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int gf_patch_gather_bf16(const void* src0, int C0, const void* src1, int C1, void* out, long long ldo,
+                                    int F, int H, int W, void* stream) {
+  if (!src0 || !out || C0 <= 0 || C1 < 0 || (C1 > 0 && !src1) || (H & 1) || (W & 1) || (ldo % 4)) return GF_ERR_BAD_ARG;
+  const long long total = (long long)F * (H / 2) * (W / 2) * (C0 + C1);
+  patch_gather_kernel<<<grid_for(total, 256), 256, 0, GF_STREAM(stream)>>>(
+      (const bf16*)src0, C0, (const bf16*)src1, C1, (bf16*)out, ldo, F, H, W);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gf_unpatchify_bf16(const void* tokens, long long ldt, void* out, int C, int F, int H, int W,
+                                  void* stream) {
+  if (!tokens || !out || C <= 0 || (H & 1) || (W & 1)) return GF_ERR_BAD_ARG;
+  const long long total = (long long)C * F * H * (W / 2);
+  unpatchify_kernel<<<grid_for(total, 256), 256, 0, GF_STREAM(stream)>>>((const bf16*)tokens, ldt, (bf16*)out, C, F, H,
+                                                                         W);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gf_add_rows_bf16(const void* a, const void* b, void* y, int rows, int cols, void* stream) {
+  if (!a || !b || !y || rows <= 0 || cols <= 0) return GF_ERR_BAD_ARG;
+  add_rows_kernel<<<grid_for((long long)rows * cols, 256), 256, 0, GF_STREAM(stream)>>>((const bf16*)a, (const bf16*)b,
+                                                                                       (bf16*)y, rows, cols);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gf_silu_bf16(const void* x, void* y, long long n, void* stream) {
+  if (!x || !y || n <= 0) return GF_ERR_BAD_ARG;
+  silu_kernel<<<grid_for(n, 256), 256, 0, GF_STREAM(stream)>>>((const bf16*)x, (bf16*)y, n);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gf_cfg_euler_bf16(const void* posi, const void* nega, const void* latents, void* latents_out,
+                                 float cfg_scale, float dsigma, long long n, void* stream) {
+  if (!posi || !latents || !latents_out || n <= 0) return GF_ERR_BAD_ARG;
+  cfg_euler_kernel<<<grid_for(n, 256), 256, 0, GF_STREAM(stream)>>>((const bf16*)posi, (const bf16*)nega,
+                                                                   (const bf16*)latents, (bf16*)latents_out, cfg_scale,
+                                                                   dsigma, n);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gf_ulysses_pack_bf16(const void* x, long long ldx, void* out, int rows, int heads, int head_dim, int P,
+                                    void* stream) {
+  if (!x || !out || rows <= 0 || P <= 0 || heads % P || head_dim % 8 || (ldx % 8)) return GF_ERR_BAD_ARG;
+  const long long total = (long long)rows * heads * head_dim / 8;
+  ulysses_pack_kernel<<<grid_for(total, 256), 256, 0, GF_STREAM(stream)>>>((const bf16*)x, ldx, (bf16*)out, rows, heads,
+                                                                          head_dim, P);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gf_ulysses_unpack_bf16(const void* in, void* y, long long ldy, int rows, int heads, int head_dim, int P,
+                                      void* stream) {
+  if (!in || !y || rows <= 0 || P <= 0 || heads % P || head_dim % 8 || (ldy % 8)) return GF_ERR_BAD_ARG;
+  const long long total = (long long)rows * heads * head_dim / 8;
+  ulysses_unpack_kernel<<<grid_for(total, 256), 256, 0, GF_STREAM(stream)>>>((const bf16*)in, (bf16*)y, ldy, rows,
+                                                                            heads, head_dim, P);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,104 @@
+/* goalforce_b200.h -- C ABI of libgoalforce_b200.so: the sm_100a kernels behind the Goal Force denoising hot path.
+ *
+ * The reference (brown-palm/goal-force) is pure Python/PyTorch and has no FFI of its own; every entry point below
+ * replaces a span of torch ops in the reference and is what a maintainer would bind with ctypes.
+ * Citations are relative to the reference checkout.
+ *
+ * Conventions
+ *   - all tensors are device pointers to row-major bf16 unless stated; the caller owns every buffer (kernels never
+ *     allocate); pointers must be 16-byte aligned and row pitches ("ld*", in elements) multiples of 8;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous and re-entrant per stream;
+ *   - return value: 0 on success, a GF_ERR_* code (< 0) for rejected arguments, or a positive cudaError_t.
+ */
+#ifndef GOALFORCE_B200_H_
+#define GOALFORCE_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GF_ABI_VERSION 1
+
+#define GF_ERR_BAD_ARG (-1)      /* null pointer, misaligned pointer/pitch, unsupported size */
+#define GF_ERR_NO_DRIVER (-2)    /* cuTensorMapEncodeTiled not resolvable (no driver / no GPU) */
+#define GF_ERR_TMAP (-3)         /* tensor-map encoding failed */
+#define GF_ERR_UNSUPPORTED (-4)  /* shape outside what the kernels are built for */
+
+/* GEMM epilogues (gf_gemm_bf16 `epi`) */
+#define GF_EPI_BIAS 0       /* C = A.W^T + bias                                                */
+#define GF_EPI_BIAS_GELU 1  /* C = gelu_tanh(A.W^T + bias)          wan_video_dit.py:209-210   */
+#define GF_EPI_BIAS_SILU 2  /* C = silu(A.W^T + bias)               wan_video_dit.py:314-318   */
+#define GF_EPI_GATE_RES 3   /* C = R + gate[n]*(A.W^T + bias)       wan_video_dit.py:189-194,226-229 */
+
+int gf_abi_version(void);
+
+/* Number of SMs of the current CUDA device (148 on B200); <= 0 if no device. */
+int gf_device_sms(void);
+
+/* nn.Linear with fused tail: C[M,N] = epi(A[M,K] . W[N,K]^T).  tcgen05/TMEM/TMA GEMM.
+ * Replaces F.linear at wan_video_dit.py:141-143,147,177-179,186,229, text/time MLPs :309-320, head :259 and the
+ * k=1 Conv1d zero-conv at src/goal_force/wan_video_new.py:1564-1570.
+ * bias/gate: [N] bf16 or NULL.  R: [M,ldr] residual for GF_EPI_GATE_RES (may alias C).  N % 32 == 0, K % 8 == 0.
+ * cta_group: 1 = one CTA per 128x256 tile, 2 = CTA pair (cta_group::2) per 256x256 tile. */
+int gf_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
+                 int K, const void* bias, int epi, const void* gate, const void* R, long long ldr, int cta_group,
+                 void* stream);
+
+/* LayerNorm over the last dim (fp32 statistics) followed by either adaLN modulation or an affine transform:
+ *   weight == NULL : y = LN(x) * (1 + scale) + shift   (norm1/norm2 + modulate, wan_video_dit.py:64-65,225,228;
+ *                                                        Head, :262-268).  shift/scale: [d] bf16.
+ *   weight != NULL : y = LN(x) * weight + bias          (norm3, wan_video_dit.py:208,227)
+ * x: [rows, ldx], y: [rows, ldy]; d % 256 == 0. */
+int gf_layernorm_bf16(const void* x, long long ldx, void* y, long long ldy, int rows, int d, float eps,
+                      const void* shift, const void* scale, const void* weight, const void* bias, void* stream);
+
+/* In-place full-row RMSNorm (* weight) followed by interleaved-pair 3-D RoPE.
+ * Replaces RMSNorm.forward + rope_apply (wan_video_dit.py:92-111,141-145,177-178).
+ * x: [rows, ldx] (only the first d columns of each row are touched); weight: [d];
+ * cos_sin: [rows, head_dim/2, 2] fp32 (cos, sin) table or NULL for no rotation (cross-attention q/k). */
+int gf_rmsnorm_rope_bf16(void* x, long long ldx, int rows, int d, const void* weight, float eps,
+                         const float* cos_sin, int head_dim, void* stream);
+
+/* Multi-head attention, no mask, no dropout: O = softmax(Q K^T * scale) V per head.  tcgen05 flash attention.
+ * Replaces flash_attention() (wan_video_dit.py:28-61) for self-attention (Lk == Lq ~ 32k) and cross-attention
+ * (Lk = 512).  Element (row, head, j) of Q lives at Q[row*ldq + head*head_dim + j]; same for K, V, O.
+ * head_dim must be 128. */
+int gf_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                      void* O, long long ldo, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
+
+/* Patch gather for the (1,2,2) Conv3d patch embedding (wan_video_dit.py:307-308,341-349; ControlNet
+ * src/goal_force/wan_video_new.py:83,91-92).  Reads channels of up to two NCTHW tensors (the torch.cat([x, y]) at
+ * src/goal_force/wan_video_new.py:1457-1458 is never materialised) and writes tokens
+ *   out[(f*H2 + h)*W2 + w, c*4 + kh*2 + kw] = src[c, f, 2h+kh, 2w+kw],   H2 = H/2, W2 = W/2
+ * which is the A operand of the patch-embedding GEMM against weight.view(dim, C*4). src1 may be NULL (C1 = 0). */
+int gf_patch_gather_bf16(const void* src0, int C0, const void* src1, int C1, void* out, long long ldo, int F, int H,
+                         int W, void* stream);
+
+/* unpatchify (wan_video_dit.py:351-356): head output [L, 4*C] with column (kh*2+kw)*C + c  ->  (C, F, H, W). */
+int gf_unpatchify_bf16(const void* tokens, long long ldt, void* out, int C, int F, int H, int W, void* stream);
+
+/* y[i, :] = a[i, :] + b[:]  (bf16 add with one rounding; modulation + t_mod, wan_video_dit.py:218-219,264-267). */
+int gf_add_rows_bf16(const void* a, const void* b, void* y, int rows, int cols, void* stream);
+
+/* y = silu(x) elementwise (time_projection.0, wan_video_dit.py:319-320). */
+int gf_silu_bf16(const void* x, void* y, long long n, void* stream);
+
+/* Classifier-free guidance + flow-matching Euler step in one pass
+ * (src/goal_force/wan_video_new.py:716,721; diffsynth/schedulers/flow_match.py:72-82):
+ *   pred = nega + cfg_scale * (posi - nega)      (nega == NULL: pred = posi)
+ *   latents_out = latents + pred * dsigma         dsigma = sigma_next - sigma
+ * with bf16 rounding after every torch op of the reference. latents_out may alias latents. */
+int gf_cfg_euler_bf16(const void* posi, const void* nega, const void* latents, void* latents_out, float cfg_scale,
+                      float dsigma, long long n, void* stream);
+
+/* Ulysses layout helpers: pack [L_local, heads, 128] rows into P contiguous per-destination blocks
+ * [P][L_local][heads/P][128] (send side) and the inverse on the receive side of the output all-to-all. */
+int gf_ulysses_pack_bf16(const void* x, long long ldx, void* out, int rows, int heads, int head_dim, int P,
+                         void* stream);
+int gf_ulysses_unpack_bf16(const void* in, void* y, long long ldy, int rows, int heads, int head_dim, int P,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOALFORCE_B200_H_ */
