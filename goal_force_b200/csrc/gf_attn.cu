@@ -25,7 +25,7 @@ constexpr int AT_D = 128;                 // head dim
 constexpr int AT_BM = 128;                // query rows per tile (2 tiles per CTA)
 constexpr int AT_BN = 128;                // kv rows per block
 constexpr int AT_THREADS = 384;           // 2 softmax warpgroups + 1 service warpgroup (producer, MMA, 2 idle warps)
-constexpr int AT_SOFTMAX_REGS = 208;      // setmaxnreg budgets: 2*128*208 + 128*96 == 64K registers
+constexpr int AT_SOFTMAX_REGS = 200;      // setmaxnreg budgets: 2*128*200 + 128*96 = 63488 <= 168*384 (the CTA pool)
 constexpr int AT_SERVICE_REGS = 96;
 constexpr int AT_SLOTS = 4;               // K/V ring slots, 32 KB each
 constexpr int AT_TILE_BYTES = 128 * 128 * 2;   // 32 KB: two [128 rows][64 cols] 128B-swizzled boxes
