@@ -35,7 +35,8 @@ SIGNATURES = {
     "gf_add_rows_bf16": [_p, _p, _p, _i, _i, _p],
     "gf_silu_bf16": [_p, _p, _ll, _p],
     "gf_cfg_euler_bf16": [_p, _p, _p, _p, _f, _f, _ll, _p],
-    "gf_ulysses_pack_bf16": [_p, _ll, _p, _i, _i, _i, _i, _p],
+    "gf_timestep_embedding_bf16": [_p, _p, _i, _i, _p],
+    "gf_ulysses_pack_bf16": [_p, _ll, _p, _ll, _i, _i, _i, _i, _p],
     "gf_ulysses_unpack_bf16": [_p, _p, _ll, _i, _i, _i, _i, _p],
 }
 
@@ -73,6 +74,47 @@ def _check(rc: int, what: str) -> None:
     if rc != 0:
         name = _ERRORS.get(rc, f"cudaError {rc}")
         raise RuntimeError(f"{what} failed: {name}")
+
+
+class LaunchStats:
+    """Counts kernel launches made through this binding and, when `timing` is on, brackets every launch with CUDA
+    events on the launching stream (used by bench.py for the per-kernel roofline numbers)."""
+
+    def __init__(self):
+        self.launches = 0
+        self.timing = False
+        self.records: list = []      # (tag, start_event, end_event, work) ; work = algorithmic flops or bytes
+
+    def reset(self, timing: bool = False):
+        self.launches = 0
+        self.timing = timing
+        self.records = []
+
+    def summary(self) -> dict:
+        """tag -> {"launches", "ms", "work"}; call after torch.cuda.synchronize()."""
+        out: dict = {}
+        for tag, e0, e1, work in self.records:
+            d = out.setdefault(tag, {"launches": 0, "ms": 0.0, "work": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["work"] += work
+        return out
+
+
+STATS = LaunchStats()
+
+
+def _call(tag: str, work: float, fn, *args) -> None:
+    STATS.launches += 1
+    if STATS.timing:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        STATS.records.append((tag, e0, e1, work))
+    else:
+        rc = fn(*args)
+    _check(rc, tag)
 
 
 def _stream() -> int:
@@ -119,10 +161,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, 
         _req(residual, "residual")
         if gate is not None:
             _req(gate, "gate")
-    rc = load().gf_gemm_bf16(a.data_ptr(), _ld(a), w.data_ptr(), _ld(w), out.data_ptr(), _ld(out), M, N, K,
-                             _ptr(bias), epi, _ptr(gate), _ptr(residual),
-                             _ld(residual) if residual is not None else 0, cta_group, _stream())
-    _check(rc, "gf_gemm_bf16")
+    _call("gemm", 2.0 * M * N * K, load().gf_gemm_bf16, a.data_ptr(), _ld(a), w.data_ptr(), _ld(w), out.data_ptr(),
+          _ld(out), M, N, K, _ptr(bias), epi, _ptr(gate), _ptr(residual),
+          _ld(residual) if residual is not None else 0, cta_group, _stream())
     return out
 
 
@@ -136,9 +177,8 @@ def layernorm(x: torch.Tensor, *, eps: float, shift: torch.Tensor | None = None,
     for n, t in (("shift", shift), ("scale", scale), ("weight", weight), ("bias", bias)):
         if t is not None:
             _req(t, n)
-    rc = load().gf_layernorm_bf16(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), rows, d, eps, _ptr(shift),
-                                  _ptr(scale), _ptr(weight), _ptr(bias), _stream())
-    _check(rc, "gf_layernorm_bf16")
+    _call("layernorm", 4.0 * rows * d, load().gf_layernorm_bf16, x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), rows,
+          d, eps, _ptr(shift), _ptr(scale), _ptr(weight), _ptr(bias), _stream())
     return out
 
 
@@ -152,9 +192,8 @@ def rmsnorm_rope_(x: torch.Tensor, weight: torch.Tensor, *, eps: float, cos_sin:
         _req(cos_sin, "cos_sin", torch.float32)
         if cos_sin.shape != (rows, head_dim // 2, 2) or not cos_sin.is_contiguous():
             raise ValueError(f"cos_sin must be contiguous [rows, head_dim/2, 2], got {tuple(cos_sin.shape)}")
-    rc = load().gf_rmsnorm_rope_bf16(x.data_ptr(), _ld(x), rows, d, weight.data_ptr(), eps, _ptr(cos_sin), head_dim,
-                                     _stream())
-    _check(rc, "gf_rmsnorm_rope_bf16")
+    _call("rmsnorm_rope", 4.0 * rows * d, load().gf_rmsnorm_rope_bf16, x.data_ptr(), _ld(x), rows, d,
+          weight.data_ptr(), eps, _ptr(cos_sin), head_dim, _stream())
     return x
 
 
@@ -168,9 +207,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, 
         out = torch.empty((Lq, heads * head_dim), dtype=torch.bfloat16, device=q.device)
     if scale is None:
         scale = head_dim ** -0.5
-    rc = load().gf_attention_bf16(q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(),
-                                  _ld(out), Lq, Lk, heads, head_dim, scale, _stream())
-    _check(rc, "gf_attention_bf16")
+    _call("attention_self" if Lk >= Lq else "attention_cross", 4.0 * Lq * Lk * heads * head_dim,
+          load().gf_attention_bf16, q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(),
+          _ld(out), Lq, Lk, heads, head_dim, scale, _stream())
     return out
 
 
@@ -189,9 +228,8 @@ def patch_gather(src0: torch.Tensor, src1: torch.Tensor | None, out: torch.Tenso
     L = F * (H // 2) * (W // 2)
     if out is None:
         out = torch.empty((L, (C0 + C1) * 4), dtype=torch.bfloat16, device=src0.device)
-    rc = load().gf_patch_gather_bf16(src0.data_ptr(), C0, _ptr(src1), C1, out.data_ptr(), _ld(out), F, H, W,
-                                     _stream())
-    _check(rc, "gf_patch_gather_bf16")
+    _call("patch_gather", 4.0 * out.numel(), load().gf_patch_gather_bf16, src0.data_ptr(), C0, _ptr(src1), C1,
+          out.data_ptr(), _ld(out), F, H, W, _stream())
     return out
 
 
@@ -199,8 +237,8 @@ def unpatchify(tokens: torch.Tensor, C: int, F: int, H: int, W: int, out: torch.
     _req(tokens, "tokens")
     if out is None:
         out = torch.empty((C, F, H, W), dtype=torch.bfloat16, device=tokens.device)
-    rc = load().gf_unpatchify_bf16(tokens.data_ptr(), _ld(tokens), out.data_ptr(), C, F, H, W, _stream())
-    _check(rc, "gf_unpatchify_bf16")
+    _call("unpatchify", 4.0 * out.numel(), load().gf_unpatchify_bf16, tokens.data_ptr(), _ld(tokens), out.data_ptr(),
+          C, F, H, W, _stream())
     return out
 
 
@@ -209,8 +247,8 @@ def add_rows(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) 
     a2 = a.reshape(-1, b.numel())
     if out is None:
         out = torch.empty_like(a2)
-    rc = load().gf_add_rows_bf16(a2.data_ptr(), b.data_ptr(), out.data_ptr(), a2.shape[0], a2.shape[1], _stream())
-    _check(rc, "gf_add_rows_bf16")
+    _call("elementwise", 4.0 * a2.numel(), load().gf_add_rows_bf16, a2.data_ptr(), b.data_ptr(), out.data_ptr(),
+          a2.shape[0], a2.shape[1], _stream())
     return out.view(a.shape)
 
 
@@ -218,8 +256,7 @@ def silu(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     _req(x, "x")
     if out is None:
         out = torch.empty_like(x)
-    rc = load().gf_silu_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream())
-    _check(rc, "gf_silu_bf16")
+    _call("elementwise", 4.0 * x.numel(), load().gf_silu_bf16, x.data_ptr(), out.data_ptr(), x.numel(), _stream())
     return out
 
 
@@ -230,20 +267,33 @@ def cfg_euler(posi: torch.Tensor, nega: torch.Tensor | None, latents: torch.Tens
         _req(nega, "nega")
     if out is None:
         out = torch.empty_like(latents)
-    rc = load().gf_cfg_euler_bf16(posi.data_ptr(), _ptr(nega), latents.data_ptr(), out.data_ptr(), cfg_scale, dsigma,
-                                  latents.numel(), _stream())
-    _check(rc, "gf_cfg_euler_bf16")
+    _call("cfg_euler", 8.0 * latents.numel(), load().gf_cfg_euler_bf16, posi.data_ptr(), _ptr(nega),
+          latents.data_ptr(), out.data_ptr(), cfg_scale, dsigma, latents.numel(), _stream())
     return out
 
 
-def ulysses_pack(x: torch.Tensor, heads: int, head_dim: int, P: int, out: torch.Tensor | None = None) -> torch.Tensor:
-    """x[rows, >=heads*head_dim] -> out[P, rows, heads/P, head_dim] (contiguous per-destination blocks)."""
+def timestep_embedding(timestep: torch.Tensor, dim: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    _req(timestep, "timestep")
+    B = timestep.numel()
+    if out is None:
+        out = torch.empty((B, dim), dtype=torch.bfloat16, device=timestep.device)
+    _call("elementwise", 2.0 * B * dim, load().gf_timestep_embedding_bf16, timestep.data_ptr(), out.data_ptr(), B, dim,
+          _stream())
+    return out
+
+
+def ulysses_pack(x: torch.Tensor, heads: int, head_dim: int, P: int, out: torch.Tensor | None = None,
+                 out_pitch: int | None = None) -> torch.Tensor:
+    """x[rows, >=heads*head_dim] -> out[P, rows, out_pitch]; destination p gets heads [p*heads/P, (p+1)*heads/P).
+    `out` may be a view into a wider send buffer (its data_ptr is the first element written)."""
     _req(x, "x")
     rows = x.shape[0]
+    width = (heads // P) * head_dim
+    out_pitch = width if out_pitch is None else out_pitch
     if out is None:
-        out = torch.empty((P, rows, heads // P, head_dim), dtype=torch.bfloat16, device=x.device)
-    rc = load().gf_ulysses_pack_bf16(x.data_ptr(), _ld(x), out.data_ptr(), rows, heads, head_dim, P, _stream())
-    _check(rc, "gf_ulysses_pack_bf16")
+        out = torch.empty((P, rows, out_pitch), dtype=torch.bfloat16, device=x.device)
+    _call("ulysses_pack", 4.0 * rows * heads * head_dim, load().gf_ulysses_pack_bf16, x.data_ptr(), _ld(x),
+          out.data_ptr(), out_pitch, rows, heads, head_dim, P, _stream())
     return out
 
 
@@ -253,6 +303,6 @@ def ulysses_unpack(inp: torch.Tensor, rows: int, heads: int, head_dim: int, P: i
     _req(inp, "inp")
     if out is None:
         out = torch.empty((rows, heads * head_dim), dtype=torch.bfloat16, device=inp.device)
-    rc = load().gf_ulysses_unpack_bf16(inp.data_ptr(), out.data_ptr(), _ld(out), rows, heads, head_dim, P, _stream())
-    _check(rc, "gf_ulysses_unpack_bf16")
+    _call("ulysses_pack", 4.0 * rows * heads * head_dim, load().gf_ulysses_unpack_bf16, inp.data_ptr(), out.data_ptr(),
+          _ld(out), rows, heads, head_dim, P, _stream())
     return out

@@ -79,9 +79,9 @@ __global__ void cfg_euler_kernel(const __nv_bfloat16* __restrict__ posi, const _
   }
 }
 
-// x[rows, heads, hd] (row pitch ldx) -> out[P][rows][heads/P][hd]; 16-byte vectors
+// x[rows, heads, hd] (row pitch ldx) -> out[P][rows][ldo >= heads/P*hd]; 16-byte vectors
 __global__ void ulysses_pack_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out,
-                                    int rows, int heads, int hd, int P) {
+                                    long long ldo, int rows, int heads, int hd, int P) {
   const int vec_per_row = heads * hd / 8;
   const int hp = heads / P;
   const int vec_per_head = hd / 8;
@@ -93,7 +93,7 @@ __global__ void ulysses_pack_kernel(const __nv_bfloat16* __restrict__ x, long lo
     const int head = vcol / vec_per_head, j = vcol % vec_per_head;
     const int dst = head / hp, hl = head % hp;
     const uint4 v = *reinterpret_cast<const uint4*>(x + row * ldx + (long long)vcol * 8);
-    *reinterpret_cast<uint4*>(out + ((((long long)dst * rows + row) * hp + hl) * hd) + j * 8) = v;
+    *reinterpret_cast<uint4*>(out + ((long long)dst * rows + row) * ldo + hl * hd + j * 8) = v;
   }
 }
 // in[P][rows][heads/P][hd] -> y[rows, heads, hd] (row pitch ldy)
@@ -111,6 +111,19 @@ __global__ void ulysses_unpack_kernel(const __nv_bfloat16* __restrict__ in, __nv
     const int src = head / hp, hl = head % hp;
     const uint4 v = *reinterpret_cast<const uint4*>(in + ((((long long)src * rows + row) * hp + hl) * hd) + j * 8);
     *reinterpret_cast<uint4*>(y + row * ldy + (long long)vcol * 8) = v;
+  }
+}
+
+// sinusoidal_embedding_1d (wan_video_dit.py:68-72): float64 angles t * 10000^(-i/half), [cos | sin], cast to bf16
+__global__ void timestep_embedding_kernel(const __nv_bfloat16* __restrict__ t, __nv_bfloat16* __restrict__ out, int B,
+                                          int dim) {
+  const int half = dim / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half; i += gridDim.x * blockDim.x) {
+    const int b = i / half, k = i % half;
+    const double pos = (double)__bfloat162float(t[b]);
+    const double ang = pos * pow(10000.0, -((double)k / (double)half));
+    out[(long long)b * dim + k] = __float2bfloat16_rn((float)cos(ang));
+    out[(long long)b * dim + half + k] = __float2bfloat16_rn((float)sin(ang));
   }
 }
 
@@ -159,6 +172,13 @@ extern "C" int gf_silu_bf16(const void* x, void* y, long long n, void* stream) {
   return (int)cudaGetLastError();
 }
 
+extern "C" int gf_timestep_embedding_bf16(const void* timestep, void* out, int B, int dim, void* stream) {
+  if (!timestep || !out || B <= 0 || dim <= 0 || (dim & 1)) return GF_ERR_BAD_ARG;
+  timestep_embedding_kernel<<<grid_for((long long)B * dim / 2, 128), 128, 0, GF_STREAM(stream)>>>(
+      (const bf16*)timestep, (bf16*)out, B, dim);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int gf_cfg_euler_bf16(const void* posi, const void* nega, const void* latents, void* latents_out,
                                  float cfg_scale, float dsigma, long long n, void* stream) {
   if (!posi || !latents || !latents_out || n <= 0) return GF_ERR_BAD_ARG;
@@ -168,12 +188,13 @@ extern "C" int gf_cfg_euler_bf16(const void* posi, const void* nega, const void*
   return (int)cudaGetLastError();
 }
 
-extern "C" int gf_ulysses_pack_bf16(const void* x, long long ldx, void* out, int rows, int heads, int head_dim, int P,
-                                    void* stream) {
-  if (!x || !out || rows <= 0 || P <= 0 || heads % P || head_dim % 8 || (ldx % 8)) return GF_ERR_BAD_ARG;
+extern "C" int gf_ulysses_pack_bf16(const void* x, long long ldx, void* out, long long ldo, int rows, int heads,
+                                    int head_dim, int P, void* stream) {
+  if (!x || !out || rows <= 0 || P <= 0 || heads % P || head_dim % 8 || (ldx % 8) || (ldo % 8)) return GF_ERR_BAD_ARG;
+  if (ldo < (long long)(heads / P) * head_dim) return GF_ERR_BAD_ARG;
   const long long total = (long long)rows * heads * head_dim / 8;
-  ulysses_pack_kernel<<<grid_for(total, 256), 256, 0, GF_STREAM(stream)>>>((const bf16*)x, ldx, (bf16*)out, rows, heads,
-                                                                          head_dim, P);
+  ulysses_pack_kernel<<<grid_for(total, 256), 256, 0, GF_STREAM(stream)>>>((const bf16*)x, ldx, (bf16*)out, ldo, rows,
+                                                                          heads, head_dim, P);
   return (int)cudaGetLastError();
 }
 

@@ -1,0 +1,531 @@
+"""B200-native Wan DiT expert and goal-force ControlNet behind the reference's call signatures.
+
+Mirrors (names, argument meaning, error behaviour):
+  * WanModel.forward(x, timestep, context, clip_feature=None, y=None, **kw)   diffsynth/models/wan_video_dit.py:358-411
+  * model_fn_wan_video(dit=, latents=, timestep=, context=, y=, controlnet=, control_signal_video_latents=, **kw)
+                                                                           src/goal_force/wan_video_new.py:1349-1591
+  * ControlNet(num_layers, stride)                                         src/goal_force/wan_video_new.py:97-117
+Weights come in as a reference state_dict (same key names); linear weights are re-laid-out once (q|k|v fused, the
+cross-attention k|v fused, conv weights flattened to GEMM operands). All compute runs in libgoalforce_b200.so through
+goal_force_b200.capi; torch only owns memory and streams. There is no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+from . import capi
+
+
+@dataclass(frozen=True)
+class DiTConfig:
+    """kwargs tables of the reference: wan_video_dit.py:502-514 (Wan2.1 T2V 1.3B), :703-718 (Wan2.2 I2V A14B)."""
+    dim: int
+    in_dim: int
+    ffn_dim: int
+    out_dim: int
+    text_dim: int
+    freq_dim: int
+    eps: float
+    num_heads: int
+    num_layers: int
+    patch_size: tuple = (1, 2, 2)
+
+    @property
+    def head_dim(self) -> int:
+        return self.dim // self.num_heads
+
+
+WAN21_T2V_1_3B = DiTConfig(dim=1536, in_dim=16, ffn_dim=8960, out_dim=16, text_dim=4096, freq_dim=256, eps=1e-6,
+                           num_heads=12, num_layers=30)
+WAN22_I2V_A14B = DiTConfig(dim=5120, in_dim=36, ffn_dim=13824, out_dim=16, text_dim=4096, freq_dim=256, eps=1e-6,
+                           num_heads=40, num_layers=40)
+
+
+def _check_cfg(cfg: DiTConfig) -> None:
+    if cfg.head_dim != 128:
+        raise ValueError(f"head_dim must be 128 (got {cfg.head_dim}): the attention kernel is built for Wan's 128")
+    if tuple(cfg.patch_size) != (1, 2, 2):
+        raise ValueError("patch_size must be (1, 2, 2)")
+    if cfg.dim % 256 or cfg.ffn_dim % 32:
+        raise ValueError("dim must be a multiple of 256 and ffn_dim of 32")
+
+
+def rope_cos_sin(head_dim: int, f: int, h: int, w: int, device, token_slice: slice | None = None) -> torch.Tensor:
+    """(cos, sin) table [f*h*w, head_dim/2, 2] fp32 for the kernels, from the reference's float64 recipe
+    (precompute_freqs_cis_3d, wan_video_dit.py:75-89, assembled as in :380-384): per-axis angles pos * theta^(-2j/dim)
+    with dims head_dim-2*(head_dim//3), head_dim//3, head_dim//3; cos/sin taken in float64, rounded once to fp32."""
+    third = head_dim // 3
+    dims = (head_dim - 2 * third, third, third)
+
+    def axis(dim: int, n: int) -> torch.Tensor:
+        inv = 1.0 / (10000.0 ** (torch.arange(0, dim, 2)[: dim // 2].double() / dim))
+        return torch.outer(torch.arange(n).double(), inv)                       # (n, dim/2) float64 angles
+
+    af, ah, aw = axis(dims[0], f), axis(dims[1], h), axis(dims[2], w)
+    ang = torch.cat([
+        af.view(f, 1, 1, -1).expand(f, h, w, -1),
+        ah.view(1, h, 1, -1).expand(f, h, w, -1),
+        aw.view(1, 1, w, -1).expand(f, h, w, -1),
+    ], dim=-1).reshape(f * h * w, head_dim // 2)
+    if token_slice is not None:
+        ang = ang[token_slice]
+    return torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).float().contiguous().to(device)
+
+
+class _Block:
+    """Weights of one DiTBlock (wan_video_dit.py:196-212) in kernel layout."""
+    __slots__ = ("wqkv", "bqkv", "norm_q", "norm_k", "wo", "bo", "cq_w", "cq_b", "cnorm_q", "cnorm_k", "ckv_w",
+                 "ckv_b", "co_w", "co_b", "n3w", "n3b", "w1", "b1", "w2", "b2", "modulation")
+
+    @classmethod
+    def from_state_dict(cls, sd: dict, pre: str, device) -> "_Block":
+        def g(name):
+            return sd[pre + name].detach().to(device=device, dtype=torch.bfloat16).contiguous()
+
+        b = cls()
+        sa, ca = "self_attn.", "cross_attn."
+        b.wqkv = torch.cat([g(sa + "q.weight"), g(sa + "k.weight"), g(sa + "v.weight")], 0).contiguous()
+        b.bqkv = torch.cat([g(sa + "q.bias"), g(sa + "k.bias"), g(sa + "v.bias")], 0).contiguous()
+        b.norm_q, b.norm_k = g(sa + "norm_q.weight"), g(sa + "norm_k.weight")
+        b.wo, b.bo = g(sa + "o.weight"), g(sa + "o.bias")
+        b.cq_w, b.cq_b = g(ca + "q.weight"), g(ca + "q.bias")
+        b.cnorm_q, b.cnorm_k = g(ca + "norm_q.weight"), g(ca + "norm_k.weight")
+        b.ckv_w = torch.cat([g(ca + "k.weight"), g(ca + "v.weight")], 0).contiguous()
+        b.ckv_b = torch.cat([g(ca + "k.bias"), g(ca + "v.bias")], 0).contiguous()
+        b.co_w, b.co_b = g(ca + "o.weight"), g(ca + "o.bias")
+        b.n3w, b.n3b = g("norm3.weight"), g("norm3.bias")
+        b.w1, b.b1 = g("ffn.0.weight"), g("ffn.0.bias")
+        b.w2, b.b2 = g("ffn.2.weight"), g("ffn.2.bias")
+        b.modulation = g("modulation").reshape(-1)          # (6*dim,)
+        return b
+
+
+class _Workspace:
+    """Activation buffers for one token count; reused across blocks, steps and experts."""
+
+    def __init__(self, L: int, cfg: DiTConfig, device):
+        d = cfg.dim
+        bf = dict(dtype=torch.bfloat16, device=device)
+        self.L = L
+        self.h = torch.empty((L, d), **bf)
+        self.qkv = torch.empty((L, 3 * d), **bf)
+        self.ao = torch.empty((L, d), **bf)
+        self.qc = torch.empty((L, d), **bf)
+        self.u = torch.empty((L, cfg.ffn_dim), **bf)
+
+
+_WORKSPACES: dict = {}
+
+
+def _workspace(L: int, cfg: DiTConfig, device) -> _Workspace:
+    key = (L, cfg.dim, cfg.ffn_dim, str(device))
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        if len(_WORKSPACES) > 4:
+            _WORKSPACES.clear()
+        ws = _Workspace(L, cfg, device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+class SequenceParallel:
+    """Ulysses sequence parallelism over one torch.distributed group (replaces
+    diffsynth/distributed/xdit_context_parallel.py:42-131 and the xfuser dependency).
+    Tokens are split contiguously over ranks; per self-attention one all-to-all moves q,k,v from
+    [L/P, heads] to [L, heads/P] and one brings the output back."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self._bufs: dict = {}
+
+    def token_slice(self, L: int) -> slice:
+        if L % self.size:
+            raise ValueError(f"token count {L} must divide evenly over {self.size} sequence-parallel ranks")
+        n = L // self.size
+        return slice(self.rank * n, (self.rank + 1) * n)
+
+    def buffers(self, Ll: int, d: int, device):
+        key = (Ll, d, str(device))
+        b = self._bufs.get(key)
+        if b is None:
+            P = self.size
+            bf = dict(dtype=torch.bfloat16, device=device)
+            b = (torch.empty((P, Ll, 3 * d // P), **bf), torch.empty((P * Ll, 3 * d // P), **bf),
+                 torch.empty((P * Ll, d // P), **bf), torch.empty((P, Ll, d // P), **bf))
+            self._bufs = {key: b}
+        return b
+
+    def self_attention(self, qkv: torch.Tensor, heads: int, out: torch.Tensor) -> None:
+        """qkv: [L/P, 3*d] (q|k|v, already normed + roped) -> out [L/P, d]."""
+        P, Ll = self.size, qkv.shape[0]
+        d = qkv.shape[1] // 3
+        hp = heads // P
+        if heads % P:
+            raise ValueError(f"{heads} heads do not divide over {P} ranks")
+        send, recv, o_full, o_recv = self.buffers(Ll, d, qkv.device)
+        w = hp * 128
+        for s in range(3):
+            capi.ulysses_pack(qkv[:, s * d:(s + 1) * d], heads, 128, P, out=send[:, :, s * w:], out_pitch=3 * w)
+        self.dist.all_to_all_single(recv.view(P, Ll, 3 * w), send, group=self.group)
+        capi.attention(recv[:, :w], recv[:, w:2 * w], recv[:, 2 * w:], hp, out=o_full)
+        self.dist.all_to_all_single(o_recv, o_full.view(P, Ll, w), group=self.group)
+        capi.ulysses_unpack(o_recv, Ll, heads, 128, P, out=out)
+
+
+def run_block(bw: _Block, cfg: DiTConfig, x: torch.Tensor, ctx_kv: torch.Tensor, mod: torch.Tensor,
+              cos_sin: torch.Tensor, ws: _Workspace, sp: SequenceParallel | None = None) -> None:
+    """DiTBlock.forward (wan_video_dit.py:214-230) in place on x [L, dim].
+    mod: [6, dim] = modulation + t_mod (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp);
+    ctx_kv: [ctx_len, 2*dim] cached cross-attention keys (RMS-normed) | values of this block."""
+    d, H, eps = cfg.dim, cfg.num_heads, cfg.eps
+    L = x.shape[0]
+    h, qkv, ao, qc, u = ws.h[:L], ws.qkv[:L], ws.ao[:L], ws.qc[:L], ws.u[:L]
+    # --- self attention
+    capi.layernorm(x, eps=eps, shift=mod[0], scale=mod[1], out=h)
+    capi.gemm(h, bw.wqkv, bw.bqkv, out=qkv)
+    capi.rmsnorm_rope_(qkv[:, :d], bw.norm_q, eps=eps, cos_sin=cos_sin, head_dim=128)
+    capi.rmsnorm_rope_(qkv[:, d:2 * d], bw.norm_k, eps=eps, cos_sin=cos_sin, head_dim=128)
+    if sp is None or sp.size == 1:
+        capi.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], H, out=ao)
+    else:
+        sp.self_attention(qkv, H, ao)
+    capi.gemm(ao, bw.wo, bw.bo, epi=capi.GF_EPI_GATE_RES, gate=mod[2], residual=x, out=x)
+    # --- cross attention
+    capi.layernorm(x, eps=eps, weight=bw.n3w, bias=bw.n3b, out=h)
+    capi.gemm(h, bw.cq_w, bw.cq_b, out=qc)
+    capi.rmsnorm_rope_(qc, bw.cnorm_q, eps=eps, cos_sin=None, head_dim=128)
+    capi.attention(qc, ctx_kv[:, :d], ctx_kv[:, d:], H, out=ao)
+    capi.gemm(ao, bw.co_w, bw.co_b, epi=capi.GF_EPI_GATE_RES, gate=None, residual=x, out=x)
+    # --- ffn
+    capi.layernorm(x, eps=eps, shift=mod[3], scale=mod[4], out=h)
+    capi.gemm(h, bw.w1, bw.b1, epi=capi.GF_EPI_BIAS_GELU, out=u)
+    capi.gemm(u, bw.w2, bw.b2, epi=capi.GF_EPI_GATE_RES, gate=mod[5], residual=x, out=x)
+
+
+def block_context_kv(bw: _Block, cfg: DiTConfig, ctx_emb: torch.Tensor) -> torch.Tensor:
+    """Cross-attention k = RMSNorm(Wk ctx + b) * w and v = Wv ctx + b (wan_video_dit.py:178-179) for one block.
+    Depends only on the prompt and the expert, not on the denoising step."""
+    kv = capi.gemm(ctx_emb, bw.ckv_w, bw.ckv_b)
+    capi.rmsnorm_rope_(kv[:, :cfg.dim], bw.cnorm_k, eps=cfg.eps, cos_sin=None, head_dim=128)
+    return kv
+
+
+class WanModelB200:
+    """Drop-in for the reference WanModel on the denoising path (inference, bf16, has_image_input=False)."""
+
+    def __init__(self, cfg: DiTConfig, state_dict: dict, device="cuda"):
+        _check_cfg(cfg)
+        capi.load()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        # attribute surface the reference pipeline reads
+        self.dim, self.in_dim, self.freq_dim, self.patch_size = cfg.dim, cfg.in_dim, cfg.freq_dim, cfg.patch_size
+        self.has_image_input = False
+        self.require_vae_embedding = True
+        self.require_clip_embedding = False
+        self.seperated_timestep = False
+        self.fuse_vae_embedding_in_latents = False
+        self.has_image_pos_emb = False
+        self.control_adapter = None
+        sd = state_dict
+
+        def g(name):
+            return sd[name].detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
+
+        self.patch_w = g("patch_embedding.weight").reshape(cfg.dim, -1).contiguous()     # (dim, in_dim*4)
+        if self.patch_w.shape[1] != cfg.in_dim * 4:
+            raise ValueError("patch_embedding.weight does not match in_dim")
+        self.patch_b = g("patch_embedding.bias")
+        self.text0_w, self.text0_b = g("text_embedding.0.weight"), g("text_embedding.0.bias")
+        self.text2_w, self.text2_b = g("text_embedding.2.weight"), g("text_embedding.2.bias")
+        self.time0_w, self.time0_b = g("time_embedding.0.weight"), g("time_embedding.0.bias")
+        self.time2_w, self.time2_b = g("time_embedding.2.weight"), g("time_embedding.2.bias")
+        self.tproj_w, self.tproj_b = g("time_projection.1.weight"), g("time_projection.1.bias")
+        self.blocks = [_Block.from_state_dict(sd, f"blocks.{i}.", self.device) for i in range(cfg.num_layers)]
+        self.block_mod = torch.stack([b.modulation for b in self.blocks], 0).contiguous()   # (layers, 6*dim)
+        self.head_w, self.head_b = g("head.head.weight"), g("head.head.bias")
+        self.head_mod = g("head.modulation").reshape(2, cfg.dim).contiguous()
+        self._ctx_cache: dict = {}
+        self._rope_cache: dict = {}
+
+    # -------------------------------------------------------------------------------------------- construction
+    @classmethod
+    def from_reference(cls, module, device="cuda") -> "WanModelB200":
+        """Build from a reference diffsynth WanModel instance (weights are copied to bf16 kernel layout)."""
+        if getattr(module, "has_image_input", False):
+            raise NotImplementedError("has_image_input=True (CLIP image branch) is outside the goal-force hot path")
+        blk = module.blocks[0]
+        cfg = DiTConfig(dim=module.dim, in_dim=module.in_dim, ffn_dim=blk.ffn_dim, out_dim=module.head.head.out_features // 4,
+                        text_dim=module.text_embedding[0].in_features, freq_dim=module.freq_dim,
+                        eps=blk.norm1.eps, num_heads=blk.num_heads, num_layers=len(module.blocks),
+                        patch_size=tuple(module.patch_size))
+        return cls(cfg, module.state_dict(), device=device)
+
+    # -------------------------------------------------------------------------------------------- step-invariant
+    def rope(self, f: int, h: int, w: int, sp: SequenceParallel | None = None) -> torch.Tensor:
+        key = (f, h, w, sp.rank if sp else 0, sp.size if sp else 1)
+        t = self._rope_cache.get(key)
+        if t is None:
+            sl = sp.token_slice(f * h * w) if sp is not None and sp.size > 1 else None
+            t = rope_cos_sin(self.cfg.head_dim, f, h, w, self.device, sl)
+            self._rope_cache = {key: t}
+        return t
+
+    def context_kv(self, context: torch.Tensor) -> list:
+        """text_embedding (wan_video_dit.py:309-313,371) + per-block cross-attention K/V, cached per context tensor
+        (the pipeline passes the same prompt embedding at every step)."""
+        key = (context.data_ptr(), context._version, tuple(context.shape))
+        hit = self._ctx_cache.get(key)      # the cached entry keeps `context` alive, so the key cannot be recycled
+        if hit is not None:
+            return hit[1]
+        ctx = context.reshape(-1, context.shape[-1]).to(device=self.device, dtype=torch.bfloat16).contiguous()
+        e = capi.gemm(ctx, self.text0_w, self.text0_b, epi=capi.GF_EPI_BIAS_GELU)
+        e = capi.gemm(e, self.text2_w, self.text2_b)
+        kvs = [block_context_kv(b, self.cfg, e) for b in self.blocks]
+        if len(self._ctx_cache) >= 4:
+            self._ctx_cache.clear()
+        self._ctx_cache[key] = (context, kvs, e)
+        return kvs
+
+    def context_embedding(self, context: torch.Tensor) -> torch.Tensor:
+        self.context_kv(context)
+        key = (context.data_ptr(), context._version, tuple(context.shape))
+        return self._ctx_cache[key][2]
+
+    def time_modulation(self, timestep: torch.Tensor):
+        """t = time_embedding(sinusoidal(timestep)); t_mod = time_projection(t) (wan_video_dit.py:368-370);
+        returns (block table [layers, 6, dim] = modulation + t_mod, head table [2, dim] = head.modulation + t)."""
+        cfg = self.cfg
+        ts = timestep.reshape(-1)[:1].to(device=self.device, dtype=torch.bfloat16).contiguous()
+        e = capi.timestep_embedding(ts, cfg.freq_dim)
+        t = capi.gemm(e, self.time0_w, self.time0_b, epi=capi.GF_EPI_BIAS_SILU)
+        t = capi.gemm(t, self.time2_w, self.time2_b)                       # (1, dim)
+        t_mod = capi.gemm(capi.silu(t), self.tproj_w, self.tproj_b)        # (1, 6*dim)
+        block_tab = capi.add_rows(self.block_mod, t_mod.reshape(-1)).view(cfg.num_layers, 6, cfg.dim)
+        head_tab = capi.add_rows(self.head_mod, t.reshape(-1)).view(2, cfg.dim)
+        return block_tab, head_tab, t_mod.reshape(-1)
+
+    # -------------------------------------------------------------------------------------------- pieces
+    def patchify(self, x: torch.Tensor, y: torch.Tensor | None = None):
+        """patch_embedding Conv3d + 'b c f h w -> b (f h w) c' for one sample: x (C0,F,H,W) [+ y (C1,F,H,W)]."""
+        tok = capi.patch_gather(x, y)
+        if tok.shape[1] != self.patch_w.shape[1]:
+            raise ValueError(f"got {tok.shape[1] // 4} input channels, patch_embedding expects {self.cfg.in_dim}")
+        F, H, W = x.shape[1:]
+        return capi.gemm(tok, self.patch_w, self.patch_b), (F, H // 2, W // 2)
+
+    def head_tokens(self, x: torch.Tensor, head_tab: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Head.forward (wan_video_dit.py:262-269) on a (local) token range -> [rows, 4*out_dim]."""
+        cfg = self.cfg
+        ws = _workspace(x.shape[0], cfg, self.device)
+        hn = capi.layernorm(x, eps=cfg.eps, shift=head_tab[0], scale=head_tab[1], out=ws.h[:x.shape[0]])
+        return capi.gemm(hn, self.head_w, self.head_b, out=out)
+
+    def unpatchify(self, tok: torch.Tensor, grid) -> torch.Tensor:
+        """WanModel.unpatchify (wan_video_dit.py:351-356) -> (out_dim, F, 2h, 2w)."""
+        f, h, w = grid
+        return capi.unpatchify(tok, self.cfg.out_dim, f, 2 * h, 2 * w)
+
+    # -------------------------------------------------------------------------------------------- forward
+    def forward(self, x, timestep, context, clip_feature=None, y=None, use_gradient_checkpointing=False,
+                use_gradient_checkpointing_offload=False, **kwargs):
+        """WanModel.forward signature (wan_video_dit.py:358-367). For A14B the reference ignores clip_feature and y
+        here (has_image_input=False) and expects x to carry all in_dim channels; like model_fn_wan_video (:1457) we
+        additionally concatenate y when x alone does not have in_dim channels."""
+        if use_gradient_checkpointing or use_gradient_checkpointing_offload:
+            raise NotImplementedError("goal_force_b200 is an inference path; gradient checkpointing is not supported")
+        yy = y if (y is not None and x.shape[1] != self.cfg.in_dim) else None
+        return model_fn_wan_video(dit=self, latents=x, timestep=timestep, context=context, y=yy)
+
+    __call__ = forward
+
+    def parameters(self):
+        for b in self.blocks:
+            for n in _Block.__slots__:
+                yield getattr(b, n)
+
+
+class _PrefixTolerant:
+    """state-dict view that accepts keys with or without a checkpoint prefix (load_controlnet_weights strips
+    'pipe.controlnet.', src/goal_force/wan_video_new.py:176-178)."""
+
+    def __init__(self, sd, prefix: str):
+        self.sd, self.prefix = sd, prefix
+
+    def __getitem__(self, key):
+        try:
+            return self.sd[key]
+        except KeyError:
+            return self.sd[self.prefix + key]
+
+
+class ControlNetB200:
+    """goal-force ControlNet (src/goal_force/wan_video_new.py:97-117) in kernel layout.
+    state-dict keys: controlnet_patch_embedding.patch_embedding.*, controlnet_dit.blocks.N.*,
+    controlnet_zero_convs_after.N.{weight (dim,dim,1), bias}; a leading 'pipe.controlnet.' is stripped as in
+    load_controlnet_weights (:176-178)."""
+
+    def __init__(self, cfg: DiTConfig, state_dict: dict, num_layers: int, stride=None, device="cuda"):
+        _check_cfg(cfg)
+        self.cfg, self.num_layers, self.stride = cfg, num_layers, stride
+        self.device = torch.device(device)
+        sd = _PrefixTolerant(state_dict, "pipe.controlnet.")
+
+        def g(name):
+            return sd[name].detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
+
+        self.patch_w = g("controlnet_patch_embedding.patch_embedding.weight").reshape(cfg.dim, -1).contiguous()
+        self.patch_b = g("controlnet_patch_embedding.patch_embedding.bias")
+        self.blocks = [_Block.from_state_dict(sd, f"controlnet_dit.blocks.{i}.", self.device) for i in range(num_layers)]
+        self.block_mod = torch.stack([b.modulation for b in self.blocks], 0).contiguous() if num_layers else None
+        self.zero_w = [g(f"controlnet_zero_convs_after.{i}.weight").reshape(cfg.dim, cfg.dim).contiguous()
+                       for i in range(num_layers)]
+        self.zero_b = [g(f"controlnet_zero_convs_after.{i}.bias") for i in range(num_layers)]
+        # F6: an untrained / never-loaded ControlNet has all-zero zero-convs; its branch is then an exact no-op
+        self.is_noop = stride is None and all(bool((w == 0).all()) and bool((b == 0).all())
+                                              for w, b in zip(self.zero_w, self.zero_b))
+        self._patch_cache: dict = {}
+        self._ctx_cache: dict = {}
+
+    @classmethod
+    def from_reference(cls, module, device="cuda") -> "ControlNetB200":
+        blk = module.controlnet_dit.blocks[0]
+        cfg = DiTConfig(dim=blk.dim, in_dim=16, ffn_dim=blk.ffn_dim, out_dim=16,
+                        text_dim=4096, freq_dim=256, eps=blk.norm1.eps, num_heads=blk.num_heads,
+                        num_layers=module.num_layers)
+        return cls(cfg, module.state_dict(), module.num_layers, stride=module.stride, device=device)
+
+    def control_tokens(self, control_latents: torch.Tensor) -> torch.Tensor:
+        """ControlNet_PatchEmbedding (wan_video_new.py:72-94); step-invariant, cached per latent tensor."""
+        key = (control_latents.data_ptr(), control_latents._version, tuple(control_latents.shape))
+        hit = self._patch_cache.get(key)    # entry keeps the latent tensor alive
+        if hit is not None:
+            return hit[1]
+        c = control_latents
+        if c.dim() == 5:
+            if c.shape[0] != 1:
+                raise NotImplementedError("control_signal_video_latents batch > 1")
+            c = c[0]
+        c = c.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        tok = capi.gemm(capi.patch_gather(c, None), self.patch_w, self.patch_b)
+        self._patch_cache = {key: (control_latents, tok)}
+        return tok
+
+    def context_kv(self, ctx_key, ctx_emb: torch.Tensor) -> list:
+        hit = self._ctx_cache.get(ctx_key)
+        if hit is None:
+            hit = [block_context_kv(b, self.cfg, ctx_emb) for b in self.blocks]
+            if len(self._ctx_cache) >= 4:
+                self._ctx_cache.clear()
+            self._ctx_cache[ctx_key] = hit
+        return hit
+
+
+_CONVERTED: dict = {}
+
+
+def _as_b200(obj, kind):
+    """Accept our classes, or reference nn.Modules (converted once and cached by identity)."""
+    if obj is None or isinstance(obj, kind):
+        return obj
+    hit = _CONVERTED.get(id(obj))
+    if hit is not None and hit[0] is obj:
+        return hit[1]
+    dev = "cuda"
+    conv = kind.from_reference(obj, device=dev)
+    _CONVERTED[id(obj)] = (obj, conv)
+    return conv
+
+
+def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None, timestep=None, context=None,
+                       clip_feature=None, y=None, reference_latents=None, vace_context=None, vace_scale=1.0,
+                       audio_embeds=None, motion_latents=None, s2v_pose_latents=None, drop_motion_frames=True,
+                       tea_cache=None, use_unified_sequence_parallel=False, motion_bucket_id=None,
+                       sliding_window_size=None, sliding_window_stride=None, cfg_merge=False,
+                       use_gradient_checkpointing=False, use_gradient_checkpointing_offload=False,
+                       control_camera_latents_input=None, fuse_vae_embedding_in_latents=False, controlnet=None,
+                       sequence_parallel: SequenceParallel | None = None, **kwargs):
+    """Drop-in for pipe.model_fn (src/goal_force/wan_video_new.py:1349-1591), goal-force configuration.
+
+    Same keyword surface as the reference; extra keywords are accepted and ignored (the pipeline passes its whole
+    shared-input dict). Options that select other Wan variants raise NotImplementedError instead of silently
+    computing something else. Returns a new (B, out_dim, F, H, W) bf16 tensor; inputs are not modified.
+    `dit` / `controlnet` may be WanModelB200 / ControlNetB200 or the reference nn.Modules (converted on first use).
+    """
+    for name, val in (("motion_controller", motion_controller if motion_bucket_id is not None else None),
+                      ("vace_context", vace_context), ("audio_embeds", audio_embeds),
+                      ("reference_latents", reference_latents), ("tea_cache", tea_cache),
+                      ("sliding_window_size", sliding_window_size),
+                      ("control_camera_latents_input", control_camera_latents_input)):
+        if val is not None:
+            raise NotImplementedError(f"{name} is outside the goal-force hot path implemented by goal_force_b200")
+    if use_gradient_checkpointing or use_gradient_checkpointing_offload:
+        raise NotImplementedError("inference only")
+    if latents is None or timestep is None or context is None:
+        raise ValueError("latents, timestep and context are required")
+    dit = _as_b200(dit, WanModelB200)
+    controlnet = _as_b200(controlnet, ControlNetB200)
+    if clip_feature is not None and dit.require_clip_embedding:
+        raise NotImplementedError("clip_feature branch (has_image_input) is not part of the A14B hot path")
+    cfg = dit.cfg
+    sp = sequence_parallel if (sequence_parallel is not None and sequence_parallel.size > 1) else None
+
+    B = max(latents.shape[0], context.shape[0])            # merged-CFG batches replicate latents (:1451-1454)
+    outs = []
+    block_tab, head_tab, t_mod_flat = dit.time_modulation(timestep)
+    for b in range(B):
+        lat = latents[min(b, latents.shape[0] - 1)].to(device=dit.device, dtype=torch.bfloat16).contiguous()
+        yb = None
+        if y is not None and dit.require_vae_embedding:
+            yb = y[min(b, y.shape[0] - 1)].to(device=dit.device, dtype=torch.bfloat16).contiguous()
+        ctx_b = context[b:b + 1] if context.shape[0] > 1 else context
+        ctx_kv = dit.context_kv(ctx_b)
+        x, (f, h, w) = dit.patchify(lat, yb)                                                    # :1464
+        L = f * h * w
+        if sp is not None:
+            x = x[sp.token_slice(L)].contiguous()                                               # :1526-1531
+        cos_sin = dit.rope(f, h, w, sp)
+        ws = _workspace(x.shape[0], cfg, dit.device)
+
+        states = None
+        use_cn = controlnet is not None and not controlnet.is_noop
+        if use_cn:                                                                              # :1489-1522
+            csl = kwargs.get("control_signal_video_latents", None)
+            if csl is None:
+                raise ValueError("controlnet given but control_signal_video_latents is missing")
+            s = controlnet.control_tokens(csl)
+            if s.shape[0] != L:
+                raise ValueError("control latents and latents have different token counts")
+            s = (s[sp.token_slice(L)] if sp is not None else s).clone()
+            ckey = (ctx_b.data_ptr(), ctx_b._version, id(dit))
+            cn_kv = controlnet.context_kv(ckey, dit.context_embedding(ctx_b))
+            # ControlNet blocks share t_mod with the trunk but carry their own modulation tables
+            cn_tab = capi.add_rows(controlnet.block_mod, t_mod_flat).view(controlnet.num_layers, 6, cfg.dim)
+            states = []
+            for i, bw in enumerate(controlnet.blocks):
+                run_block(bw, cfg, s, cn_kv[i], cn_tab[i], cos_sin, ws, sp)
+                states.append(s.clone() if i + 1 < controlnet.num_layers else s)
+
+        for i, bw in enumerate(dit.blocks):                                                     # :1540-1570
+            run_block(bw, cfg, x, ctx_kv[i], block_tab[i], cos_sin, ws, sp)
+            if use_cn:
+                if controlnet.stride is not None:
+                    if i % controlnet.stride == 0 and i // controlnet.stride < len(states):
+                        capi.add_rows(x.view(1, -1), states[i // controlnet.stride].view(-1), out=x.view(1, -1))
+                elif i < controlnet.num_layers:
+                    capi.gemm(states[i], controlnet.zero_w[i], controlnet.zero_b[i], epi=capi.GF_EPI_GATE_RES,
+                              gate=None, residual=x, out=x)
+        tok = dit.head_tokens(x, head_tab)                                                      # :1581
+        if sp is not None:                                                                      # :1582-1585
+            full = torch.empty((L, tok.shape[1]), dtype=torch.bfloat16, device=dit.device)
+            sp.dist.all_gather_into_tensor(full, tok, group=sp.group)
+            tok = full
+        outs.append(dit.unpatchify(tok, (f, h, w)))                                             # :1590
+    return torch.stack(outs, 0)

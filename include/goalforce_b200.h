@@ -91,10 +91,18 @@ int gf_silu_bf16(const void* x, void* y, long long n, void* stream);
 int gf_cfg_euler_bf16(const void* posi, const void* nega, const void* latents, void* latents_out, float cfg_scale,
                       float dsigma, long long n, void* stream);
 
-/* Ulysses layout helpers: pack [L_local, heads, 128] rows into P contiguous per-destination blocks
- * [P][L_local][heads/P][128] (send side) and the inverse on the receive side of the output all-to-all. */
-int gf_ulysses_pack_bf16(const void* x, long long ldx, void* out, int rows, int heads, int head_dim, int P,
-                         void* stream);
+/* sinusoidal_embedding_1d (wan_video_dit.py:68-72): out[b, :] = [cos(t_b w_i) | sin(t_b w_i)], w_i = 10000^(-i/(dim/2)),
+ * angles in float64, result rounded to bf16. timestep: [B] bf16 on the device (no host sync). */
+int gf_timestep_embedding_bf16(const void* timestep, void* out, int B, int dim, void* stream);
+
+/* Ulysses layout helpers (replace the head<->sequence reshuffles inside xfuser's long-context attention called at
+ * diffsynth/distributed/xdit_context_parallel.py:121-126).
+ * pack:   x[rows, heads*head_dim] (pitch ldx) -> out[P][rows][ldo], destination rank p receives heads
+ *         [p*heads/P, (p+1)*heads/P) in the first heads/P*head_dim elements of each out row (ldo lets q, k, v share
+ *         one send buffer).
+ * unpack: in[P][rows][heads/P*head_dim] (source-rank major) -> y[rows, heads*head_dim] (pitch ldy). */
+int gf_ulysses_pack_bf16(const void* x, long long ldx, void* out, long long ldo, int rows, int heads, int head_dim,
+                         int P, void* stream);
 int gf_ulysses_unpack_bf16(const void* in, void* y, long long ldy, int rows, int heads, int head_dim, int P,
                            void* stream);
 

@@ -1,0 +1,172 @@
+"""Generate tests/golden/* by running the UNMODIFIED reference from /root/reference on CPU -- TEST INFRASTRUCTURE ONLY.
+
+    python -m oracle.gen_golden            # writes tests/golden/{dit_*.pt, scheduler.json, control_channels.json}
+
+The fixtures hold inputs and reference outputs only; weights are re-created from a seed by
+oracle.wan_dit_oracle.random_state_dict (a pure torch.Generator recipe), so the files stay small.
+Every vector here was produced by reference code: WanModel / model_fn_wan_video / ControlNet
+(src/goal_force/wan_video_new.py, diffsynth/models/wan_video_dit.py), FlowMatchScheduler
+(diffsynth/schedulers/flow_match.py) and ControlSignalDataset_Balls (src/goal_force/unified_dataset.py).
+"""
+from __future__ import annotations
+
+import glob
+import json
+import os
+import shutil
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import control_channels_oracle as CC
+from . import ref_shim
+from . import wan_dit_oracle as O
+
+GOLDEN = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+TINY = O.DiTConfig(dim=256, in_dim=36, ffn_dim=512, out_dim=16, text_dim=64, freq_dim=256, eps=1e-6, num_heads=2,
+                   num_layers=2)
+TINY_T2V = O.DiTConfig(dim=256, in_dim=16, ffn_dim=512, out_dim=16, text_dim=64, freq_dim=256, eps=1e-6, num_heads=2,
+                       num_layers=3)
+# ControlNet_DiT hard-codes the A14B widths (src/goal_force/wan_video_new.py:56-60), so the ControlNet golden has to
+# be A14B-wide; two trunk blocks + one ControlNet block keep it runnable on CPU.
+A14B_SLICE = O.DiTConfig(dim=5120, in_dim=36, ffn_dim=13824, out_dim=16, text_dim=4096, freq_dim=256, eps=1e-6,
+                         num_heads=40, num_layers=2)
+
+
+def _ref_model(ns, cfg, sd):
+    m = ns.WanModel(**ref_shim.cfg_kwargs(cfg)).eval()
+    m.load_state_dict(sd, strict=True)
+    return m
+
+
+def gen_dit(ns):
+    out = {}
+    with torch.no_grad():
+        # 1) tiny I2V-shaped model, model_fn without ControlNet, fp32 and bf16, plus WanModel.forward equivalence (F8)
+        for name, cfg, shape in (("tiny_i2v", TINY, (3, 8, 12)), ("tiny_t2v", TINY_T2V, (2, 6, 10))):
+            sd = O.random_state_dict(cfg, seed=0)
+            inp = O.synthetic_inputs(cfg, *shape, seed=1, ctx_len=32, ctx_valid=8, timestep=937.0)
+            m = _ref_model(ns, cfg, sd)
+            kw = dict(latents=inp["latents"], timestep=inp["timestep"], context=inp["context"])
+            if "y" in inp:
+                kw["y"] = inp["y"]
+            ref = ns.model_fn_wan_video(dit=m, **kw)
+            x_in = torch.cat([inp["latents"], inp["y"]], 1) if "y" in inp else inp["latents"]
+            fwd = m(x_in, inp["timestep"], inp["context"])
+            assert torch.equal(ref, fwd), "model_fn != WanModel.forward(cat[x,y]) (SURVEY F8)"
+            mb = _ref_model(ns, cfg, sd).to(torch.bfloat16)
+            kwb = {k: v.to(torch.bfloat16) for k, v in kw.items()}
+            ref_bf16 = ns.model_fn_wan_video(dit=mb, **kwb)
+            out[name] = dict(cfg=cfg.__dict__, weight_seed=0, input_seed=1, shape=shape, ctx_len=32, ctx_valid=8,
+                             timestep=937.0, out_fp32=ref, out_bf16=ref_bf16)
+            print(name, "fp32-vs-bf16 relL2", O.rel_l2(ref_bf16, ref))
+        # 2) A14B-wide slice with the reference ControlNet (non-zero zero-convs) and the zero-conv no-op invariant
+        cfg = A14B_SLICE
+        sd = O.random_state_dict(cfg, seed=0)
+        csd = O.random_controlnet_state_dict(cfg, 1, seed=1)
+        inp = O.synthetic_inputs(cfg, 2, 8, 12, seed=1, ctx_len=32, ctx_valid=8, timestep=937.0)
+        m = _ref_model(ns, cfg, sd)
+        cn = ns.ControlNet(1, stride=None, torch_dtype=torch.float32).eval()
+        cn.load_state_dict(csd, strict=True)
+        kw = dict(latents=inp["latents"], timestep=inp["timestep"], context=inp["context"], y=inp["y"])
+        base = ns.model_fn_wan_video(dit=m, **kw)
+        with_cn = ns.model_fn_wan_video(dit=m, controlnet=cn,
+                                        control_signal_video_latents=inp["control_signal_video_latents"], **kw)
+        czero = O.random_controlnet_state_dict(cfg, 1, seed=1, zero_convs=True)
+        cn.load_state_dict(czero, strict=True)
+        noop = ns.model_fn_wan_video(dit=m, controlnet=cn,
+                                     control_signal_video_latents=inp["control_signal_video_latents"], **kw)
+        assert torch.equal(noop, base), "zero-conv ControlNet is not a no-op"
+        out["a14b_slice_controlnet"] = dict(cfg=cfg.__dict__, weight_seed=0, controlnet_seed=1, input_seed=1,
+                                            shape=(2, 8, 12), ctx_len=32, ctx_valid=8, timestep=937.0,
+                                            out_fp32=with_cn, out_base_fp32=base)
+        print("a14b slice: controlnet effect relL2", O.rel_l2(with_cn, base))
+    torch.save(out, GOLDEN / "dit_forward.pt")
+
+
+def gen_scheduler(ns):
+    res = {}
+    for steps, shift in ((40, 5.0), (50, 5.0), (4, 5.0)):
+        s = ns.FlowMatchScheduler(shift=5, sigma_min=0.0, extra_one_step=True)   # as WanVideoPipeline.__init__ (:129)
+        s.set_timesteps(steps, denoising_strength=1.0, shift=shift)
+        n_high = int((s.timesteps >= 875).sum())
+        # one Euler step on a fixed bf16 sample through the reference scheduler
+        g = torch.Generator("cpu").manual_seed(3)
+        sample = torch.randn(2, 3, 4, generator=g).bfloat16()
+        pred = torch.randn(2, 3, 4, generator=g).bfloat16()
+        stepped = [s.step(pred, s.timesteps[i], sample).float().tolist() for i in (0, steps // 2, steps - 1)]
+        res[f"{steps}_{shift}"] = dict(sigmas=s.sigmas.tolist(), timesteps=s.timesteps.tolist(), n_high_noise=n_high,
+                                       sample=sample.float().tolist(), pred=pred.float().tolist(), stepped=stepped)
+    (GOLDEN / "scheduler.json").write_text(json.dumps(res))
+
+
+def _dataset_overrides(ds):
+    # scripts/inference/inference_goal_force.py:137-144
+    ds.min_mass, ds.max_mass = 1.0, 4.0
+    ds.min_force, ds.max_force = 30.0, 400.0
+    ds.min_indirect_force, ds.max_indirect_force = ds.min_force, ds.max_force
+
+
+def gen_control_channels():
+    import pandas
+    ud = ref_shim.load_dataset_module()
+    csvs = sorted(glob.glob(os.path.join(ref_shim.REFERENCE_ROOT, "datasets/examples/*/*.csv")))
+    csvs = [c for c in csvs if "canny" not in c]
+    res = {"goal_force": {}, "direct_force": {}, "rows": {}}
+    tmp = Path(tempfile.mkdtemp(prefix="gf_golden_"))
+    try:
+        for csv in csvs:
+            name = os.path.basename(csv).split("_obj")[0]
+            ds = ud.ControlSignalDataset_Balls(base_path=os.path.dirname(csv), metadata_path=csv,
+                                               is_validation_dataset=True, num_frames=81, height=480, width=832)
+            _dataset_overrides(ds)
+            np.random.seed(0)
+            cv = ds[0]["control_video"]
+            res["goal_force"][name] = CC.digest(cv)
+            row = pandas.read_csv(csv).iloc[0].to_dict()
+            res["rows"][name] = {k: (v.item() if hasattr(v, "item") else v) for k, v in row.items() if k != "caption"}
+            # direct-force variant: give the projectile a force + mass, drop the goal force
+            df = pandas.read_csv(csv)
+            for col in ("projectile_force_magnitude", "projectile_force_angle", "projectile_mass",
+                        "target_indirect_force_magnitude"):
+                df[col] = df[col].astype(float)
+            df.loc[0, "projectile_force_magnitude"] = 250.0
+            df.loc[0, "projectile_force_angle"] = 37.0
+            df.loc[0, "projectile_mass"] = 2.5
+            df.loc[0, "target_indirect_force_magnitude"] = -1
+            d = tmp / name
+            (d / "images").mkdir(parents=True)
+            img = df.loc[0, "image"]
+            os.symlink(os.path.join(os.path.dirname(csv), "images", img), d / "images" / img)
+            df.to_csv(d / "row.csv", index=False)
+            ds2 = ud.ControlSignalDataset_Balls(base_path=str(d), metadata_path=str(d / "row.csv"),
+                                                is_validation_dataset=True, num_frames=81, height=480, width=832)
+            _dataset_overrides(ds2)
+            np.random.seed(0)
+            cv2 = ds2[0]["control_video"]
+            res["direct_force"][name] = CC.digest(cv2)
+            print(name, res["goal_force"][name], res["direct_force"][name], tuple(cv.shape))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    (GOLDEN / "control_channels.json").write_text(json.dumps(res, indent=1))
+
+
+def main():
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ns = ref_shim.load()
+    import sys
+    what = sys.argv[1:] or ["scheduler", "dit", "control"]
+    if "scheduler" in what:
+        gen_scheduler(ns)
+    if "dit" in what:
+        gen_dit(ns)
+    if "control" in what:
+        gen_control_channels()
+
+
+if __name__ == "__main__":
+    main()

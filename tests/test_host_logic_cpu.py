@@ -1,0 +1,103 @@
+"""Host-side logic of the product that runs without a GPU: scheduler table, control channels (bit-exact), mask
+construction, parallel layout, RoPE table, weight re-layout."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from goal_force_b200 import control_channels as P
+from goal_force_b200.pipeline import ParallelLayout, first_frame_mask, generate_noise, image_condition, latent_shape
+from goal_force_b200.scheduler import FlowMatchScheduler
+from goal_force_b200.wan_dit import rope_cos_sin
+from oracle import control_channels_oracle as CC
+from oracle import wan_dit_oracle as O
+
+
+@pytest.mark.parametrize("steps", [40, 50, 4])
+def test_scheduler_matches_reference_table(golden_dir, steps):
+    g = json.loads((golden_dir / "scheduler.json").read_text())[f"{steps}_5.0"]
+    s = FlowMatchScheduler(shift=5, sigma_min=0.0, extra_one_step=True)
+    s.set_timesteps(steps, shift=5.0)
+    assert s.sigmas.tolist() == g["sigmas"]              # bit-exact fp32 table
+    assert s.timesteps.tolist() == g["timesteps"]
+    assert int((s.timesteps >= 875).sum()) == g["n_high_noise"]
+    # dsigma picks the same neighbours as the reference's step(); last step goes to sigma 0
+    assert s.dsigma(s.timesteps[0]) == float(torch.tensor(g["sigmas"][1]) - torch.tensor(g["sigmas"][0]))
+    assert s.dsigma(s.timesteps[-1]) == float(torch.zeros(()) - torch.tensor(g["sigmas"][-1]))
+
+
+def test_expert_split_counts():
+    # 40 steps -> 17 high-noise / 23 low-noise; 50 steps -> 21 / 29
+    for steps, high in ((40, 17), (50, 21)):
+        s = FlowMatchScheduler()
+        s.set_timesteps(steps, shift=5.0)
+        assert int((s.timesteps >= 0.875 * 1000).sum()) == high
+
+
+def test_control_channels_bit_exact_all_examples(golden_dir):
+    g = json.loads((golden_dir / "control_channels.json").read_text())
+    assert len(g["goal_force"]) == 12
+    for name, want in g["goal_force"].items():
+        np.random.seed(0)
+        cv = P.control_video_from_csv_row(g["rows"][name])
+        assert CC.digest(cv) == want, name
+    for name in ("_pendulum", "_toycar", "_cantaloupes", "_paw_tool2"):
+        row = dict(g["rows"][name])
+        row.update(projectile_force_magnitude=250.0, projectile_force_angle=37.0, projectile_mass=2.5,
+                   target_indirect_force_magnitude=-1.0)
+        np.random.seed(0)
+        cv = P.control_video_from_csv_row(row)
+        assert CC.digest(cv) == g["direct_force"][name], name
+        assert float(cv[..., 1].abs().max()) == 0.0 and float(cv[..., 0].max()) > 0.9
+
+
+def test_control_channels_both_forces_consumes_rng_like_reference():
+    row = dict(projectile_force_magnitude=100.0, projectile_force_angle=10.0, projectile_coordx=100, projectile_coordy=50,
+               projectile_mass=2.0, target_indirect_force_angle=200.0, target_indirect_force_magnitude=300.0,
+               target_coordx=300, target_coordy=80, target_mass=3.0, width=208, height=120)
+    kw = dict(num_frames=5, height=120, width=208, min_force=30., max_force=400., min_indirect_force=30.,
+              max_indirect_force=400., min_mass=1., max_mass=4., p_mask_out_direct_force=0.3,
+              p_mask_out_indirect_force=0.3, p_mask_out_masses=0.5)
+    for seed in range(6):
+        r1, r2 = np.random.RandomState(seed), np.random.RandomState(seed)
+        a = CC.control_video(**CC.row_to_args(row), rng=r1, **kw)
+        b = P.generate_control_video(P.ControlSignalSpec.from_csv_row(row), rng=r2, **kw)
+        assert torch.equal(a, b)
+        assert r1.uniform() == r2.uniform()              # same number of draws consumed
+
+
+def test_first_frame_mask_and_condition():
+    m = first_frame_mask(81, 6, 8)
+    assert m.shape == (4, 21, 6, 8)
+    assert float(m[:, 0].min()) == 1.0 and float(m[:, 1:].max()) == 0.0
+    m2 = first_frame_mask(81, 6, 8, end_image=True)
+    assert float(m2[3, -1].min()) == 1.0 and float(m2[:3, -1].max()) == 0.0
+    y = image_condition(torch.randn(16, 21, 6, 8), 81)
+    assert y.shape == (1, 20, 21, 6, 8)
+    assert latent_shape(81, 480, 832) == (1, 16, 21, 60, 104)
+
+
+def test_generate_noise_is_seed_reproducible_on_cpu():
+    a = generate_noise((1, 16, 2, 4, 4), seed=5, device="cpu")
+    g = torch.Generator("cpu").manual_seed(5)
+    b = torch.randn((1, 16, 2, 4, 4), generator=g, dtype=torch.float32).to(torch.bfloat16)
+    assert torch.equal(a, b)
+
+
+def test_parallel_layout():
+    lay = ParallelLayout(world_size=8, rank=5, cfg_size=2)
+    assert (lay.sp_size, lay.cfg_index, lay.sp_index) == (4, 1, 1)
+    assert lay.sp_ranks() == [4, 5, 6, 7] and lay.cfg_ranks() == [1, 5]
+    with pytest.raises(ValueError):
+        ParallelLayout(world_size=3, rank=0, cfg_size=2)
+
+
+def test_rope_table_matches_oracle_freqs():
+    f, h, w = 3, 4, 5
+    cs = rope_cos_sin(128, f, h, w, "cpu")
+    fr = O.rope_freqs(128, f, h, w, "cpu")[:, 0]
+    assert cs.shape == (60, 64, 2)
+    assert torch.equal(cs[..., 0], fr.real.float()) and torch.equal(cs[..., 1], fr.imag.float())
+    sl = slice(20, 40)
+    assert torch.equal(rope_cos_sin(128, f, h, w, "cpu", sl), cs[sl])
