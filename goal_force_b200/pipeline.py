@@ -140,7 +140,7 @@ class GoalForceDenoiser:
         if par is not None and par.layout.cfg_size == 2 and use_cfg:
             mine = self.model_fn(context=context_posi if par.layout.cfg_index == 0 else context_nega, **kw)
             both = torch.empty((2,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
-            par.dist.all_gather_into_tensor(both, mine.contiguous(), group=par.cfg_group)
+            par.dist.all_gather_into_tensor(both.view(-1), mine.contiguous().view(-1), group=par.cfg_group)
             posi, nega = both[0], both[1]
         else:
             posi = self.model_fn(context=context_posi, **kw)                           # :710
