@@ -5,8 +5,8 @@
 // One CTA owns 256 query rows of one head (two 128-row tiles that ping-pong through the tensor core):
 //   warps 0-3 / 4-7 : softmax warpgroup of tile 0 / tile 1.  Thread t owns query row t of its tile: it reads the
 //                     whole 128-column score row from TMEM (tcgen05.ld 32x32b, no shuffles needed for the row
-//                     max / sum), exponentiates in the log2 domain (one FFMA + one MUFU.EX2 per score), packs
-//                     P to bf16 and writes it back to TMEM over the score columns (tcgen05.st).
+//                     max / sum), exponentiates in the log2 domain, packs P to bf16 and writes it back to TMEM
+//                     over the score columns (tcgen05.st).
 //   warp 8          : TMA producer: Q once, then K_0, V_0, K_1, V_1, ... through a 4-slot shared-memory ring.
 //   warp 9          : MMA issuer (one elected thread):  S_i = Q_i K_j^T  (SS, both operands K-major in smem)
 //                                                       O_i += P_i V_j   (TS, P from TMEM, V MN-major in smem)
@@ -14,8 +14,21 @@
 // Issue order per KV block j:  PV(j,0) QK(j+1,0) PV(j,1) QK(j+1,1)  -- tcgen05.mma executes in issue order, so
 // QK(j+1,i) cannot overwrite P_i(j) before PV(j,i) consumed it, and while warpgroup i runs its softmax the tensor
 // core works on the other tile.
-// Online softmax with lazy rescaling: the running reference max only moves when the block max exceeds it by more
-// than 2^8; O is rescaled (by the softmax warp itself, straight in TMEM) only in that rare case.
+//
+// The per-tile chain softmax(j) -> PV(j) -> QK(j+1) -> softmax(j+1) is what bounds the kernel (each MMA pair is
+// 1024 tensor cycles, and 128 MUFU.EX2 per thread are 1024 cycles of one SMSP's MUFU), so the softmax is built to be
+// short:
+//   * speculative reference max: the exponentials of block j use the running reference max m_used of the previous
+//     blocks, so MUFU work starts as soon as S is in registers; the true row max of block j is computed in the
+//     shadow of the first half. Only if it exceeds m_used by more than 2^8 (rare after the first block) is the
+//     reference moved: O and l are rescaled in TMEM by the softmax warp itself and the first half is redone.
+//   * the exponent and the row sum use packed f32x2 FMA/ADD (half the issue slots);
+//   * a fixed fraction of the exponentials is evaluated on the FMA pipe instead of the MUFU
+//     (Cody-Waite split + degree-3 minimax polynomial, 7.5e-5 relative error, far below the bf16 rounding of P);
+//   * P is handed to the MMA warp in two halves, so PV(j,i) starts while the second half is still being
+//     exponentiated.
+#include <cstdlib>
+#include <type_traits>
 #include "gf_ptx.cuh"
 #include "gf_api_internal.h"
 
@@ -41,6 +54,85 @@ struct AttnParams {
   float scale_log2;      // softmax scale * log2(e)
 };
 
+// ------------------------------------------------------------------ packed f32x2 helpers (FFMA2 / FADD2 on sm_100)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// 2^x for two lanes on the FMA pipe: x = n + r, n = rint(x), r in [-0.5, 0.5];  2^r by a degree-3 minimax
+// polynomial (max relative error 7.5e-5), 2^n by adding n to the exponent field.  x is clamped to >= -125.
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
+  constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: low mantissa bits of (x + kMagic) hold rint(x)
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x0 = fmaxf(x0, -125.0f);
+  x1 = fmaxf(x1, -125.0f);
+  x2 = pack2(x0, x1);
+  const uint64_t t2 = fadd2(x2, pack2(kMagic, kMagic));
+  const uint64_t n2 = fadd2(t2, pack2(-kMagic, -kMagic));
+  const uint64_t r2 = ffma2(n2, pack2(-1.0f, -1.0f), x2);
+  uint64_t q2 = ffma2(pack2(0.0551716685295105f, 0.0551716685295105f), r2, pack2(0.2426111251115799f, 0.2426111251115799f));
+  q2 = ffma2(q2, r2, pack2(0.6932609677314758f, 0.6932609677314758f));
+  q2 = ffma2(q2, r2, pack2(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, t0, t1;
+  unpack2(q2, q0, q1);
+  unpack2(t2, t0, t1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
+// Exponentiate one 32-column chunk of a score row: p = 2^(s*scale - m), accumulate the row sum, pack to bf16.
+// kEmuPairs of the 16 column pairs go through the polynomial, spread evenly between the MUFU pairs.
+template <int kEmuPairs>
+__device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], uint64_t scale2, uint64_t negm2, uint64_t (&acc)[2],
+                                          uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const uint64_t x2 = ffma2(pack2u(s[2 * k], s[2 * k + 1]), scale2, negm2);
+    float p0, p1;
+    const bool emulate = ((k + 1) * kEmuPairs) / 16 != (k * kEmuPairs) / 16;
+    if (emulate) {
+      exp2_poly2(x2, p0, p1);
+    } else {
+      float x0, x1;
+      unpack2(x2, x0, x1);
+      p0 = ex2_approx(x0);
+      p1 = ex2_approx(x1);
+    }
+    acc[k & 1] = fadd2(acc[k & 1], pack2(p0, p1));
+    pk[k] = pack_bf16x2(p0, p1);
+  }
+}
+
+__device__ __forceinline__ float chunk_max(const uint32_t (&s)[32]) {
+  float m = fmaxf(__uint_as_float(s[0]), __uint_as_float(s[1]));
+#pragma unroll
+  for (int k = 1; k < 16; ++k) m = fmax3(m, __uint_as_float(s[2 * k]), __uint_as_float(s[2 * k + 1]));
+  return m;
+}
+
+template <int kEmuPairs>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -53,9 +145,10 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bar_base + 8u * (1 + AT_SLOTS + s); };
   auto s_full = [&](int i) { return bar_base + 8u * (1 + 2 * AT_SLOTS + i); };
-  auto p_full = [&](int i) { return bar_base + 8u * (3 + 2 * AT_SLOTS + i); };
-  auto o_done = [&](int i) { return bar_base + 8u * (5 + 2 * AT_SLOTS + i); };
-  const uint32_t tmem_ptr_smem = bar_base + 8u * (7 + 2 * AT_SLOTS);
+  auto p_half = [&](int i) { return bar_base + 8u * (3 + 2 * AT_SLOTS + i); };
+  auto p_full = [&](int i) { return bar_base + 8u * (5 + 2 * AT_SLOTS + i); };
+  auto o_done = [&](int i) { return bar_base + 8u * (7 + 2 * AT_SLOTS + i); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (9 + 2 * AT_SLOTS);
 
   const int warp = threadIdx.x >> 5;
   const int head = blockIdx.x / p.q_blocks;          // consecutive CTAs share a head's K/V in L2
@@ -78,6 +171,7 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(s_full(i), 1);
+        mbar_init(p_half(i), 128);
         mbar_init(p_full(i), 128);
         mbar_init(o_done(i), 1);
       }
@@ -145,12 +239,18 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t k_addr = kv_smem + slot_k * AT_TILE_BYTES;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
+          // 16 kv rows per MMA: 8 packed-bf16 TMEM columns of P, 2 KB of V; first half of P arrives early
+          mbar_wait(p_half(i), j & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < AT_BN / 32; ++kk)
+            umma_ts(tmem_O(i), tmem_S(i) + kk * 8, smem_desc(desc_v, v_addr + kk * 2048), idesc_pv,
+                    (j | kk) != 0 ? 1u : 0u);
           mbar_wait(p_full(i), j & 1);
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < AT_BN / 16; ++kk)   // 16 kv rows per MMA: 8 packed-bf16 TMEM columns of P, 2 KB of V
-            umma_ts(tmem_O(i), tmem_S(i) + kk * 8, smem_desc(desc_v, v_addr + kk * 2048), idesc_pv,
-                    (j | kk) != 0 ? 1u : 0u);
+          for (int kk = AT_BN / 32; kk < AT_BN / 16; ++kk)
+            umma_ts(tmem_O(i), tmem_S(i) + kk * 8, smem_desc(desc_v, v_addr + kk * 2048), idesc_pv, 1u);
           tc_commit(o_done(i));
           if (more) {
             if (i == 0) {
@@ -175,8 +275,12 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t tS = tmem_S(i) + lane_off, tO = tmem_O(i) + lane_off;
     const int row = q0 + i * AT_BM + wq * 32 + (int)lane;
     const int tail_valid = p.Lk - (n_kv - 1) * AT_BN;          // valid columns of the last kv block (1..128)
+    const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
     float m_used = 0.f, l = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
+    // One kv block.  kFirst (block 0) has no reference max yet, so it computes the row max before exponentiating;
+    // every later block exponentiates against the running reference and checks the true max in the shadow.
+    auto kv_block = [&](const int j, auto first_tag) {
+      constexpr bool kFirst = decltype(first_tag)::value;
       mbar_wait(s_full(i), j & 1);
       tc_fence_after();
       uint32_t s[4][32];
@@ -190,54 +294,69 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int k = 0; k < 32; ++k)
             if (c * 32 + k >= tail_valid) s[c][k] = 0xFF800000u;  // -inf
       }
-      float mx = __uint_as_float(s[0][0]);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(s[c][k]));
-      const float m_cur = mx * p.scale_log2;
-      bool need = false;
-      float alpha = 1.0f;
-      if (j == 0) {
-        m_used = m_cur;
-      } else if (m_cur > m_used + AT_RESCALE_THRESHOLD) {
-        need = true;
-        alpha = ex2_approx(m_used - m_cur);
-        m_used = m_cur;
+      if constexpr (kFirst)
+        m_used = fmaxf(fmaxf(chunk_max(s[0]), chunk_max(s[1])), fmaxf(chunk_max(s[2]), chunk_max(s[3]))) *
+                 p.scale_log2;
+      uint64_t acc[2] = {0ull, 0ull};
+      uint32_t pk[16];
+      {
+        const uint64_t negm2 = pack2(-m_used, -m_used);
+        exp_chunk<kEmuPairs>(s[0], scale2, negm2, acc, pk);
+        tmem_st16(tS, pk);
+        exp_chunk<kEmuPairs>(s[1], scale2, negm2, acc, pk);
+        tmem_st16(tS + 16, pk);
       }
-      if (__any_sync(0xffffffffu, need)) {
-        // rare: bring O (and l) to the new reference max. PV(j-1, i) must have landed first.
-        mbar_wait(o_done(i), (j - 1) & 1);
-        tc_fence_after();
+      if constexpr (!kFirst) {
+        // true row max of this block (log2 domain), computed in the shadow of the first half
+        const float m_cur = fmaxf(fmaxf(chunk_max(s[0]), chunk_max(s[1])), fmaxf(chunk_max(s[2]), chunk_max(s[3]))) *
+                            p.scale_log2;
+        const bool need = m_cur > m_used + AT_RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, need)) {
+          // rare: move the reference max. PV(j-1, i) must have landed before O is touched; the first half of P
+          // (computed against the stale reference) is redone.
+          const float alpha = need ? ex2_approx(m_used - m_cur) : 1.0f;
+          if (need) m_used = m_cur;
+          mbar_wait(o_done(i), (j - 1) & 1);
+          tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tO + c * 32, o);
-          tmem_ld_wait();
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO + c * 32, o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
-          tmem_st32(tO + c * 32, o);
+            for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+            tmem_st32(tO + c * 32, o);
+          }
+          l *= alpha;
+          acc[0] = 0ull; acc[1] = 0ull;
+          const uint64_t negm2 = pack2(-m_used, -m_used);
+          exp_chunk<0>(s[0], scale2, negm2, acc, pk);
+          tmem_st16(tS, pk);
+          exp_chunk<0>(s[1], scale2, negm2, acc, pk);
+          tmem_st16(tS + 16, pk);
         }
-        l *= alpha;
       }
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(s[c][2 * k]), p.scale_log2, -m_used));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(s[c][2 * k + 1]), p.scale_log2, -m_used));
-          sum += p0 + p1;
-          pk[k] = pack_bf16x2(p0, p1);
-        }
-        tmem_st16(tS + c * 16, pk);                  // P_i: packed bf16, columns [0, 64) of the S_i region
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_half(i));
+      {
+        const uint64_t negm2 = pack2(-m_used, -m_used);
+        exp_chunk<kEmuPairs>(s[2], scale2, negm2, acc, pk);
+        tmem_st16(tS + 32, pk);
+        exp_chunk<kEmuPairs>(s[3], scale2, negm2, acc, pk);
+        tmem_st16(tS + 48, pk);
       }
-      l += sum;
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full(i));
-    }
+      float a0, a1, a2, a3;
+      unpack2(acc[0], a0, a1);
+      unpack2(acc[1], a2, a3);
+      l += (a0 + a1) + (a2 + a3);
+    };
+    kv_block(0, std::true_type{});
+#pragma unroll 1
+    for (int j = 1; j < n_kv; ++j) kv_block(j, std::false_type{});
     // ---------------- epilogue: O / l -> bf16 -> global
     mbar_wait(o_done(i), (n_kv - 1) & 1);
     tc_fence_after();
@@ -269,6 +388,33 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
+// Fraction of exponentials evaluated on the FMA pipe, in column pairs per 16 (0, 2, 4, 5, 6).  Tuning knob:
+// GF_ATTN_EMU_PAIRS in the environment overrides the default (read once).
+static int attn_emu_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("GF_ATTN_EMU_PAIRS");
+    v = e ? std::atoi(e) : 4;
+    if (v != 0 && v != 2 && v != 4 && v != 5 && v != 6) v = 4;
+  }
+  return v;
+}
+
+template <int kEmuPairs>
+static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p,
+                       cudaStream_t stream) {
+  auto kern = gf_attn_kernel<kEmuPairs>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const dim3 grid(p.q_blocks * p.heads), block(AT_THREADS);
+  kern<<<grid, block, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace gf
 
 extern "C" int gf_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V,
@@ -285,19 +431,18 @@ extern "C" int gf_attention_bf16(const void* Q, long long ldq, const void* K, lo
   if (rc) return rc;
   rc = gf_make_tmap_2d_bf16(&tmV, V, (uint64_t)heads * AT_D, (uint64_t)Lk, (uint64_t)ldv, 64, AT_BN);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gf_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
   AttnParams p;
   p.O = reinterpret_cast<__nv_bfloat16*>(O);
   p.ldo = ldo;
   p.Lq = Lq; p.Lk = Lk; p.heads = heads;
   p.q_blocks = (Lq + 2 * AT_BM - 1) / (2 * AT_BM);
   p.scale_log2 = scale * 1.4426950408889634f;
-  const dim3 grid(p.q_blocks * heads), block(AT_THREADS);
-  gf_attn_kernel<<<grid, block, AT_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
-  return (int)cudaGetLastError();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (attn_emu_pairs()) {
+    case 0: return launch_attn<0>(tmQ, tmK, tmV, p, s);
+    case 2: return launch_attn<2>(tmQ, tmK, tmV, p, s);
+    case 5: return launch_attn<5>(tmQ, tmK, tmV, p, s);
+    case 6: return launch_attn<6>(tmQ, tmK, tmV, p, s);
+    default: return launch_attn<4>(tmQ, tmK, tmV, p, s);
+  }
 }

@@ -321,10 +321,65 @@ def g_rowwise_perf():
     return res
 
 
+def g_attn_one():
+    """accuracy + sustained timing of the attention kernel as configured by GF_ATTN_EMU_PAIRS (one process = one variant)"""
+    import torch
+    from goal_force_b200 import capi
+    res = {"emu_pairs": os.environ.get("GF_ATTN_EMU_PAIRS", "default")}
+    heads, d = 40, 5120
+    torch.manual_seed(0)
+    # accuracy: L = 4096, all heads, vs fp32 SDPA; plus a growing-magnitude case that forces the rescale branch
+    L = 4096
+    qkv = torch.randn(L, 3 * d, device="cuda").bfloat16()
+    o = capi.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], heads)
+    res["acc_L4096"] = _stats(o, _attn_ref(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], heads))
+    q2 = torch.randn(1000, 2 * 128, device="cuda")
+    k2 = torch.randn(1333, 2 * 128, device="cuda") * torch.linspace(0.2, 6.0, 1333, device="cuda")[:, None]
+    v2 = torch.randn(1333, 2 * 128, device="cuda")
+    q2, k2, v2 = q2.bfloat16(), k2.bfloat16(), v2.bfloat16()
+    res["acc_rescale"] = _stats(capi.attention(q2, k2, v2, 2), _attn_ref(q2, k2, v2, 2))
+    q3 = (torch.randn(300, 128, device="cuda") * 3).bfloat16()
+    k3 = (torch.randn(200, 128, device="cuda") * 3).bfloat16()
+    v3 = torch.randn(200, 128, device="cuda").bfloat16()
+    res["acc_ragged_peaky"] = _stats(capi.attention(q3, k3, v3, 1), _attn_ref(q3, k3, v3, 1))
+    L = 32760
+    qkv = torch.randn(L, 3 * d, device="cuda").bfloat16()
+    o = torch.empty(L, d, device="cuda", dtype=torch.bfloat16)
+    fl = 4.0 * L * L * d
+    run = lambda: capi.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], heads, out=o)  # noqa: E731
+    ms = timed(run, iters=3, warmup=1)
+    res["burst"] = {"ms": ms, "tflops": fl / ms / 1e9}
+    ms = timed(run, iters=40, warmup=0)          # ~0.7 s back to back: settles under the power cap
+    res["sustained"] = {"ms": ms, "tflops": fl / ms / 1e9}
+    idx = torch.randint(0, L, (48,), device="cuda")
+    ref = _attn_ref(qkv[idx, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], heads)
+    res["acc_L32760_rows"] = _stats(o[idx], ref)
+    kv = torch.randn(512, 2 * d, device="cuda").bfloat16()
+    q = qkv[:, :d].contiguous()
+    ms = timed(lambda: capi.attention(q, kv[:, :d], kv[:, d:], heads, out=o), iters=20)
+    res["cross"] = {"ms": ms, "tflops": 4.0 * L * 512 * d / ms / 1e9}
+    for k, v in res.items():
+        print(k, v, flush=True)
+    return res
+
+
+def g_attn_sweep():
+    res = {}
+    for emu in os.environ.get("GF_ATTN_SWEEP", "0,2,4,5,6").split(","):
+        env = dict(os.environ, GF_ATTN_EMU_PAIRS=emu, PYTHONUNBUFFERED="1")
+        r = subprocess.run([sys.executable, __file__, "attn_one"], env=env, capture_output=True, text=True, timeout=280)
+        print(f"---- GF_ATTN_EMU_PAIRS={emu} rc={r.returncode}\n{r.stdout[-2500:]}{r.stderr[-1500:]}", flush=True)
+        try:
+            res[emu] = json.loads((OUT / "check_attn_one.json").read_text())
+        except Exception:  # noqa: BLE001
+            res[emu] = {"rc": r.returncode}
+    return res
+
+
 GROUPS = {
     "gemm_small": g_gemm_small, "gemm_small2": g_gemm_small2, "gemm_epi": g_gemm_epi, "rowwise": g_rowwise,
     "misc": g_misc, "attn_small": g_attn_small, "gemm_perf": g_gemm_perf, "attn_perf": g_attn_perf,
-    "rowwise_perf": g_rowwise_perf,
+    "rowwise_perf": g_rowwise_perf, "attn_one": g_attn_one, "attn_sweep": g_attn_sweep,
 }
 
 
@@ -342,7 +397,7 @@ def main():
         log = OUT / f"check_{name}.log"
         with open(log, "w") as f:
             try:
-                r = subprocess.run([sys.executable, __file__, name], stdout=f, stderr=subprocess.STDOUT, timeout=300,
+                r = subprocess.run([sys.executable, __file__, name], stdout=f, stderr=subprocess.STDOUT, timeout=1500,
                                    env=dict(os.environ, PYTHONUNBUFFERED="1"))
                 rc = r.returncode
             except subprocess.TimeoutExpired:
