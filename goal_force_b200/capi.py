@@ -29,6 +29,7 @@ SIGNATURES = {
     "gf_gemm_bf16": [_p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p, _i, _p, _p, _ll, _i, _p],
     "gf_layernorm_bf16": [_p, _ll, _p, _ll, _i, _i, _f, _p, _p, _p, _p, _p],
     "gf_rmsnorm_rope_bf16": [_p, _ll, _i, _i, _p, _f, _p, _i, _p],
+    "gf_qk_rmsnorm_rope_bf16": [_p, _ll, _i, _i, _p, _p, _f, _p, _i, _p],
     "gf_attention_bf16": [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _f, _p],
     "gf_patch_gather_bf16": [_p, _i, _p, _i, _p, _ll, _i, _i, _i, _p],
     "gf_unpatchify_bf16": [_p, _ll, _p, _i, _i, _i, _i, _p],
@@ -195,6 +196,22 @@ def rmsnorm_rope_(x: torch.Tensor, weight: torch.Tensor, *, eps: float, cos_sin:
     _call("rmsnorm_rope", 4.0 * rows * d, load().gf_rmsnorm_rope_bf16, x.data_ptr(), _ld(x), rows, d,
           weight.data_ptr(), eps, _ptr(cos_sin), head_dim, _stream())
     return x
+
+
+def qk_rmsnorm_rope_(qkv: torch.Tensor, weight_q: torch.Tensor, weight_k: torch.Tensor, *, eps: float,
+                     cos_sin: torch.Tensor | None, head_dim: int) -> torch.Tensor:
+    """In place on the q (columns [0,d)) and k (columns [d,2d)) parts of a fused q|k|v buffer, one launch."""
+    _req(qkv, "qkv"); _req(weight_q, "weight_q"); _req(weight_k, "weight_k")
+    rows, d = qkv.shape[0], weight_q.numel()
+    if qkv.shape[1] < 2 * d or weight_k.numel() != d:
+        raise ValueError("qkv must hold at least q|k of width d each")
+    if cos_sin is not None:
+        _req(cos_sin, "cos_sin", torch.float32)
+        if cos_sin.shape != (rows, head_dim // 2, 2) or not cos_sin.is_contiguous():
+            raise ValueError(f"cos_sin must be contiguous [rows, head_dim/2, 2], got {tuple(cos_sin.shape)}")
+    _call("rmsnorm_rope", 8.0 * rows * d, load().gf_qk_rmsnorm_rope_bf16, qkv.data_ptr(), _ld(qkv), rows, d,
+          weight_q.data_ptr(), weight_k.data_ptr(), eps, _ptr(cos_sin), head_dim, _stream())
+    return qkv
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, out: torch.Tensor | None = None,

@@ -1,12 +1,15 @@
 // gf_rowwise.cu -- the HBM-bound kernels of the DiT block: adaLN LayerNorm and full-row RMSNorm + 3-D RoPE.
-// One warp owns one row: the row (d bf16, d % 256 == 0) is read once with 128-bit loads, kept packed in registers,
-// reduced with warp shuffles, and written once with 128-bit stores.  Algorithmic traffic = 2 * rows * d * 2 bytes.
+// A row (d bf16) is split over TPR threads (128 for d = 5120): every thread keeps NVT 128-bit vectors of the row
+// in registers, so the row is read once (streaming 128-bit loads) and written once (128-bit stores); statistics are
+// reduced with warp shuffles plus one shared-memory exchange between the warps of a row.  Few registers per thread
+// (about 50) keep 40+ warps resident per SM, which is what hides HBM latency; a 256-thread CTA carries 256/TPR rows.
+// Algorithmic traffic = 2 * rows * d * 2 bytes.
 #include "gf_ptx.cuh"
 #include "gf_api_internal.h"
 
 namespace gf {
 
-constexpr int ROW_WARPS = 8;  // warps (rows) per CTA
+constexpr int ROW_THREADS = 256;  // threads per CTA
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -22,34 +25,55 @@ __device__ __forceinline__ uint4 ld_stream(const void* p) {
   return r;
 }
 
+// Sum `v` over the TPR threads that share a row. `slot` is this reduction's private shared array
+// [rows per CTA][warps per row]; one __syncthreads per call (all threads of the CTA must call it).
+template <int TPR>
+__device__ __forceinline__ float row_sum(float v, float* slot) {
+  v = warp_sum(v);
+  if constexpr (TPR == 32) {
+    return v;
+  } else {
+    constexpr int WPR = TPR / 32;
+    const int w = threadIdx.x >> 5, r = threadIdx.x / TPR;
+    if ((threadIdx.x & 31) == 0) slot[w] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < WPR; ++i) t += slot[r * WPR + i];
+    return t;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- LayerNorm
 // weight == nullptr: y = bf16(bf16(bf16(LN(x)) * bf16(1 + scale)) + shift)   (eager-PyTorch rounding chain of
 //                    modulate(norm(x), shift, scale), wan_video_dit.py:64-65)
 // weight != nullptr: y = bf16(LN(x) * weight + bias)                          (nn.LayerNorm with affine, fp32 math)
-template <int NV>  // uint4 vectors per lane: d = NV * 256
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+template <int NVT, int TPR>  // d = NVT * TPR * 8
+__global__ void __launch_bounds__(ROW_THREADS)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
                  int rows, float eps, const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
                  const __nv_bfloat16* __restrict__ weight, const __nv_bfloat16* __restrict__ bias) {
-  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  constexpr int d = NV * 256;
-  const __nv_bfloat16* xr = x + (long long)row * ldx;
-  uint4 v[NV];
+  constexpr int d = NVT * TPR * 8;
+  constexpr int RPC = ROW_THREADS / TPR;
+  __shared__ float red[2][ROW_THREADS / 32];
+  const int t = threadIdx.x % TPR;
+  const int row = blockIdx.x * RPC + threadIdx.x / TPR;
+  const bool live = row < rows;                      // dead rows still take part in the CTA barriers
+  const __nv_bfloat16* xr = x + (long long)(live ? row : 0) * ldx;
+  uint4 v[NVT];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = ld_stream(xr + (i * 32 + lane) * 8);
+  for (int i = 0; i < NVT; ++i) v[i] = ld_stream(xr + (i * TPR + t) * 8);
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
+  for (int i = 0; i < NVT; ++i) {
     const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) s += bf16_lo(w[j]) + bf16_hi(w[j]);
   }
-  const float mean = warp_sum(s) * (1.0f / d);
+  const float mean = row_sum<TPR>(s, red[0]) * (1.0f / d);
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
+  for (int i = 0; i < NVT; ++i) {
     const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -57,11 +81,12 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat
       ss += a * a + b * b;
     }
   }
-  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / d) + eps);
+  const float rstd = rsqrtf(row_sum<TPR>(ss, red[1]) * (1.0f / d) + eps);
+  if (!live) return;
   __nv_bfloat16* yr = y + (long long)row * ldy;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int col = (i * 32 + lane) * 8;
+  for (int i = 0; i < NVT; ++i) {
+    const int col = (i * TPR + t) * 8;
     const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
     uint32_t o[4];
     if (weight) {
@@ -89,43 +114,50 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat
 }
 
 // ---------------------------------------------------------------------------------------------- RMSNorm + RoPE
-// x <- rope( bf16( bf16(x * rsqrt(mean(x^2) + eps)) * weight ) )       in place, one warp per row
+// x <- rope( bf16( bf16(x * rsqrt(mean(x^2) + eps)) * weight ) )       in place
 // RoPE acts on interleaved pairs (2i, 2i+1) of every head: (a + ib) * (cos + i sin), one rounding to bf16
 // (wan_video_dit.py:92-97 does the product in complex128; fp32 FMA on an fp32 table built from the float64
 //  angles differs from that by < 1e-7 relative before the bf16 rounding).
-// Lane l always sees pairs 4l%64 .. 4l%64+3 of a head (row layout d = heads*128, 8 elements per lane per vector,
-// 256 elements per warp-wide vector), so the 4 (cos, sin) pairs are loaded once per row.
-template <int NV>
-__global__ void __launch_bounds__(ROW_WARPS * 32)
-rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int rows, float eps,
-                    const __nv_bfloat16* __restrict__ weight, const float* __restrict__ cos_sin, int half_dim) {
-  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  constexpr int d = NV * 256;
-  __nv_bfloat16* xr = x + (long long)row * ldx;
-  uint4 v[NV];
+// Thread t of a row always sees pairs 4t%64 .. 4t%64+3 of a head (head_dim 128, 8 elements per vector and TPR*8 a
+// multiple of 128), so its 4 (cos, sin) pairs are loaded once per row.
+// blockIdx.y selects a segment: segment g normalises columns [g*seg_stride, g*seg_stride + d) with weight[g]
+// (q and k of a fused qkv row in one launch; each segment has its own row statistic).
+template <int NVT, int TPR>
+__global__ void __launch_bounds__(ROW_THREADS)
+rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, long long seg_stride, int rows, float eps,
+                    const __nv_bfloat16* __restrict__ weight0, const __nv_bfloat16* __restrict__ weight1,
+                    const float* __restrict__ cos_sin, int half_dim) {
+  constexpr int d = NVT * TPR * 8;
+  constexpr int RPC = ROW_THREADS / TPR;
+  __shared__ float red[ROW_THREADS / 32];
+  const int t = threadIdx.x % TPR;
+  const int row = blockIdx.x * RPC + threadIdx.x / TPR;
+  const bool live = row < rows;
+  const __nv_bfloat16* weight = blockIdx.y ? weight1 : weight0;
+  __nv_bfloat16* xr = x + (long long)(live ? row : 0) * ldx + (long long)blockIdx.y * seg_stride;
+  uint4 v[NVT];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
+  for (int i = 0; i < NVT; ++i) v[i] = *reinterpret_cast<const uint4*>(xr + (i * TPR + t) * 8);
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
+  for (int i = 0; i < NVT; ++i) {
     const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) ss += bf16_lo(w[j]) * bf16_lo(w[j]) + bf16_hi(w[j]) * bf16_hi(w[j]);
   }
-  const float r = rsqrtf(warp_sum(ss) * (1.0f / d) + eps);
+  const float r = rsqrtf(row_sum<TPR>(ss, red) * (1.0f / d) + eps);
+  if (!live) return;
   float cs[4], sn[4];
   if (cos_sin) {
-    // head_dim == 128 => pair index of this lane's first pair inside a head: (lane*4) % 64
-    const float4* t = reinterpret_cast<const float4*>(cos_sin + ((long long)row * half_dim + (lane * 4) % half_dim) * 2);
-    const float4 t0 = __ldg(t), t1 = __ldg(t + 1);
+    // head_dim == 128 => pair index of this thread's first pair inside a head: (t*4) % 64
+    const float4* tb = reinterpret_cast<const float4*>(cos_sin + ((long long)row * half_dim + (t * 4) % half_dim) * 2);
+    const float4 t0 = __ldg(tb), t1 = __ldg(tb + 1);
     cs[0] = t0.x; sn[0] = t0.y; cs[1] = t0.z; sn[1] = t0.w;
     cs[2] = t1.x; sn[2] = t1.y; cs[3] = t1.z; sn[3] = t1.w;
   }
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int col = (i * 32 + lane) * 8;
+  for (int i = 0; i < NVT; ++i) {
+    const int col = (i * TPR + t) * 8;
     const uint4 wv = __ldg(reinterpret_cast<const uint4*>(weight + col));
     const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
     uint32_t o[4];
@@ -144,6 +176,34 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int rows, floa
   }
 }
 
+template <int NVT, int TPR>
+static void launch_ln(cudaStream_t s, const __nv_bfloat16* X, long long ldx, __nv_bfloat16* Y, long long ldy, int rows,
+                      float eps, const __nv_bfloat16* SH, const __nv_bfloat16* SC, const __nv_bfloat16* W,
+                      const __nv_bfloat16* B) {
+  constexpr int RPC = ROW_THREADS / TPR;
+  layernorm_kernel<NVT, TPR><<<(rows + RPC - 1) / RPC, ROW_THREADS, 0, s>>>(X, ldx, Y, ldy, rows, eps, SH, SC, W, B);
+}
+
+template <int NVT, int TPR>
+static void launch_rms(cudaStream_t s, __nv_bfloat16* X, long long ldx, long long seg_stride, int segs, int rows,
+                       float eps, const __nv_bfloat16* W0, const __nv_bfloat16* W1, const float* cos_sin, int half) {
+  constexpr int RPC = ROW_THREADS / TPR;
+  const dim3 grid((rows + RPC - 1) / RPC, segs);
+  rmsnorm_rope_kernel<NVT, TPR><<<grid, ROW_THREADS, 0, s>>>(X, ldx, seg_stride, rows, eps, W0, W1, cos_sin, half);
+}
+
+static int rms_dispatch(cudaStream_t s, __nv_bfloat16* X, long long ldx, long long seg_stride, int segs, int rows, int d,
+                        float eps, const __nv_bfloat16* W0, const __nv_bfloat16* W1, const float* cos_sin, int half) {
+  switch (d) {
+    case 5120: launch_rms<5, 128>(s, X, ldx, seg_stride, segs, rows, eps, W0, W1, cos_sin, half); break;
+    case 1536: launch_rms<3, 64>(s, X, ldx, seg_stride, segs, rows, eps, W0, W1, cos_sin, half); break;
+    case 512: launch_rms<2, 32>(s, X, ldx, seg_stride, segs, rows, eps, W0, W1, cos_sin, half); break;
+    case 256: launch_rms<1, 32>(s, X, ldx, seg_stride, segs, rows, eps, W0, W1, cos_sin, half); break;
+    default: return GF_ERR_UNSUPPORTED;
+  }
+  return (int)cudaGetLastError();
+}
+
 }  // namespace gf
 
 extern "C" int gf_layernorm_bf16(const void* x, long long ldx, void* y, long long ldy, int rows, int d, float eps,
@@ -152,17 +212,16 @@ extern "C" int gf_layernorm_bf16(const void* x, long long ldx, void* y, long lon
   using namespace gf;
   if (!x || !y || rows <= 0 || (ldx % 8) || (ldy % 8)) return GF_ERR_BAD_ARG;
   if (weight ? !bias : (!shift || !scale)) return GF_ERR_BAD_ARG;
-  const dim3 grid((rows + ROW_WARPS - 1) / ROW_WARPS), block(ROW_WARPS * 32);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   auto X = reinterpret_cast<const __nv_bfloat16*>(x);
   auto Y = reinterpret_cast<__nv_bfloat16*>(y);
   auto SH = reinterpret_cast<const __nv_bfloat16*>(shift), SC = reinterpret_cast<const __nv_bfloat16*>(scale);
   auto W = reinterpret_cast<const __nv_bfloat16*>(weight), B = reinterpret_cast<const __nv_bfloat16*>(bias);
   switch (d) {
-    case 5120: layernorm_kernel<20><<<grid, block, 0, s>>>(X, ldx, Y, ldy, rows, eps, SH, SC, W, B); break;
-    case 1536: layernorm_kernel<6><<<grid, block, 0, s>>>(X, ldx, Y, ldy, rows, eps, SH, SC, W, B); break;
-    case 256: layernorm_kernel<1><<<grid, block, 0, s>>>(X, ldx, Y, ldy, rows, eps, SH, SC, W, B); break;
-    case 512: layernorm_kernel<2><<<grid, block, 0, s>>>(X, ldx, Y, ldy, rows, eps, SH, SC, W, B); break;
+    case 5120: launch_ln<5, 128>(s, X, ldx, Y, ldy, rows, eps, SH, SC, W, B); break;
+    case 1536: launch_ln<3, 64>(s, X, ldx, Y, ldy, rows, eps, SH, SC, W, B); break;
+    case 512: launch_ln<2, 32>(s, X, ldx, Y, ldy, rows, eps, SH, SC, W, B); break;
+    case 256: launch_ln<1, 32>(s, X, ldx, Y, ldy, rows, eps, SH, SC, W, B); break;
     default: return GF_ERR_UNSUPPORTED;
   }
   return (int)cudaGetLastError();
@@ -173,16 +232,18 @@ extern "C" int gf_rmsnorm_rope_bf16(void* x, long long ldx, int rows, int d, con
   using namespace gf;
   if (!x || !weight || rows <= 0 || (ldx % 8)) return GF_ERR_BAD_ARG;
   if (cos_sin && head_dim != 128) return GF_ERR_UNSUPPORTED;
-  const dim3 grid((rows + ROW_WARPS - 1) / ROW_WARPS), block(ROW_WARPS * 32);
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  auto X = reinterpret_cast<__nv_bfloat16*>(x);
   auto W = reinterpret_cast<const __nv_bfloat16*>(weight);
-  switch (d) {
-    case 5120: rmsnorm_rope_kernel<20><<<grid, block, 0, s>>>(X, ldx, rows, eps, W, cos_sin, head_dim / 2); break;
-    case 1536: rmsnorm_rope_kernel<6><<<grid, block, 0, s>>>(X, ldx, rows, eps, W, cos_sin, head_dim / 2); break;
-    case 256: rmsnorm_rope_kernel<1><<<grid, block, 0, s>>>(X, ldx, rows, eps, W, cos_sin, head_dim / 2); break;
-    case 512: rmsnorm_rope_kernel<2><<<grid, block, 0, s>>>(X, ldx, rows, eps, W, cos_sin, head_dim / 2); break;
-    default: return GF_ERR_UNSUPPORTED;
-  }
-  return (int)cudaGetLastError();
+  return rms_dispatch(reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<__nv_bfloat16*>(x), ldx, 0, 1, rows, d,
+                      eps, W, W, cos_sin, head_dim / 2);
+}
+
+extern "C" int gf_qk_rmsnorm_rope_bf16(void* qkv, long long ld, int rows, int d, const void* weight_q,
+                                       const void* weight_k, float eps, const float* cos_sin, int head_dim,
+                                       void* stream) {
+  using namespace gf;
+  if (!qkv || !weight_q || !weight_k || rows <= 0 || (ld % 8) || ld < 2LL * d) return GF_ERR_BAD_ARG;
+  if (cos_sin && head_dim != 128) return GF_ERR_UNSUPPORTED;
+  return rms_dispatch(reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<__nv_bfloat16*>(qkv), ld, d, 2, rows, d,
+                      eps, reinterpret_cast<const __nv_bfloat16*>(weight_q),
+                      reinterpret_cast<const __nv_bfloat16*>(weight_k), cos_sin, head_dim / 2);
 }

@@ -190,8 +190,7 @@ def run_block(bw: _Block, cfg: DiTConfig, x: torch.Tensor, ctx_kv: torch.Tensor,
     # --- self attention
     capi.layernorm(x, eps=eps, shift=mod[0], scale=mod[1], out=h)
     capi.gemm(h, bw.wqkv, bw.bqkv, out=qkv)
-    capi.rmsnorm_rope_(qkv[:, :d], bw.norm_q, eps=eps, cos_sin=cos_sin, head_dim=128)
-    capi.rmsnorm_rope_(qkv[:, d:2 * d], bw.norm_k, eps=eps, cos_sin=cos_sin, head_dim=128)
+    capi.qk_rmsnorm_rope_(qkv, bw.norm_q, bw.norm_k, eps=eps, cos_sin=cos_sin, head_dim=128)
     if sp is None or sp.size == 1:
         capi.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], H, out=ao)
     else:

@@ -59,6 +59,12 @@ int gf_layernorm_bf16(const void* x, long long ldx, void* y, long long ldy, int 
 int gf_rmsnorm_rope_bf16(void* x, long long ldx, int rows, int d, const void* weight, float eps,
                          const float* cos_sin, int head_dim, void* stream);
 
+/* The q and k halves of a fused [rows, >= 2d] q|k|v row in one launch: columns [0,d) use weight_q, [d,2d) weight_k,
+ * each with its own full-row statistic (SelfAttention.forward, wan_video_dit.py:141-145). Same math as
+ * gf_rmsnorm_rope_bf16 applied twice. */
+int gf_qk_rmsnorm_rope_bf16(void* qkv, long long ld, int rows, int d, const void* weight_q, const void* weight_k,
+                            float eps, const float* cos_sin, int head_dim, void* stream);
+
 /* Multi-head attention, no mask, no dropout: O = softmax(Q K^T * scale) V per head.  tcgen05 flash attention.
  * Replaces flash_attention() (wan_video_dit.py:28-61) for self-attention (Lk == Lq ~ 32k) and cross-attention
  * (Lk = 512).  Element (row, head, j) of Q lives at Q[row*ldq + head*head_dim + j]; same for K, V, O.

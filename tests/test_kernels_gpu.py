@@ -101,6 +101,23 @@ def test_layernorm_and_rmsnorm_rope(capi, d):
     assert (xx != n).float().mean() < 1e-3
 
 
+@pytest.mark.parametrize("d", [5120, 1536])
+def test_fused_qk_rmsnorm_rope_equals_two_calls(capi, d):
+    torch.manual_seed(8)
+    rows = 1030                                   # ragged against the 2 / 4 rows per CTA
+    qkv = (torch.randn(rows, 3 * d, device="cuda") * 1.7).bfloat16()
+    wq, wk = torch.randn(d, device="cuda").bfloat16(), torch.randn(d, device="cuda").bfloat16()
+    ang = torch.rand(rows, 64, device="cuda", dtype=torch.float64) * 6.28
+    cs = torch.stack([ang.cos(), ang.sin()], -1).float().contiguous()
+    a = qkv.clone()
+    capi.rmsnorm_rope_(a[:, :d], wq, eps=1e-6, cos_sin=cs, head_dim=128)
+    capi.rmsnorm_rope_(a[:, d:2 * d], wk, eps=1e-6, cos_sin=cs, head_dim=128)
+    b = qkv.clone()
+    capi.qk_rmsnorm_rope_(b, wq, wk, eps=1e-6, cos_sin=cs, head_dim=128)
+    assert torch.equal(a, b)
+    assert torch.equal(b[:, 2 * d:], qkv[:, 2 * d:])          # v untouched
+
+
 def _attn_ref(q, k, v, heads):
     Lq, Lk = q.shape[0], k.shape[0]
     qh, kh, vh = (t.float().reshape(t.shape[0], heads, 128).transpose(0, 1)[None] for t in (q, k, v))

@@ -1,0 +1,81 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped on a 1-GPU box): Ulysses sequence parallel SP(P) must equal the
+single-GPU forward -- bit for bit, because every kernel is row-local except attention, and attention sees exactly
+the same per-head operands after the all-to-all -- and CFG-parallel sampling must equal sequential CFG."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, mode, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from goal_force_b200.pipeline import GoalForceDenoiser, ParallelContext, ParallelLayout
+        from goal_force_b200.wan_dit import ControlNetB200, DiTConfig, WanModelB200, model_fn_wan_video
+        from oracle import wan_dit_oracle as O
+        dev = torch.device("cuda", rank)
+        ocfg = O.DiTConfig(**{**O.WAN22_I2V_A14B.__dict__, "num_layers": 2})
+        cfg = DiTConfig(**ocfg.__dict__)
+        sd = O.random_state_dict(ocfg, seed=2)
+        csd = O.random_controlnet_state_dict(ocfg, 1, seed=3)
+        inp = {k: v.to(dev, torch.bfloat16) for k, v in O.synthetic_inputs(ocfg, 4, 40, 52, seed=4, timestep=990.0).items()}
+        dit = WanModelB200(cfg, sd, device=dev)
+        cn = ControlNetB200(cfg, csd, 1, device=dev)
+        kw = dict(dit=dit, controlnet=cn, latents=inp["latents"], timestep=inp["timestep"], context=inp["context"],
+                  y=inp["y"], control_signal_video_latents=inp["control_signal_video_latents"])
+        if mode == "sp":
+            par = ParallelContext(ParallelLayout(world_size=world, rank=rank, cfg_size=1))
+            single = model_fn_wan_video(**kw)
+            multi = model_fn_wan_video(sequence_parallel=par.sp, **kw)
+            ok = bool(torch.equal(single, multi))
+            err = float((single.float() - multi.float()).abs().max())
+        else:  # cfg axis: 2 ranks = conditional | unconditional
+            par = ParallelContext(ParallelLayout(world_size=world, rank=rank, cfg_size=2))
+            g = torch.Generator("cpu").manual_seed(13)
+            ctx_n = torch.randn(1, 512, cfg.text_dim, generator=g).to(dev, torch.bfloat16)
+            seq = GoalForceDenoiser(dit, controlnet=cn)
+            parl = GoalForceDenoiser(dit, controlnet=cn, parallel=par)
+            a = seq(inp["latents"], inp["context"], ctx_n, y=inp["y"],
+                    control_latents=inp["control_signal_video_latents"], num_inference_steps=2, cfg_scale=5.0)
+            b = parl(inp["latents"], inp["context"], ctx_n, y=inp["y"],
+                     control_latents=inp["control_signal_video_latents"], num_inference_steps=2, cfg_scale=5.0)
+            ok = bool(torch.equal(a, b))
+            err = float((a.float() - b.float()).abs().max())
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ret["ok"], ret["err"] = bool(flag.item()), err
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(mode):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), mode, ret), nprocs=2, join=True)
+    assert ret.get("ok"), f"{mode}: multi-GPU result differs from single-GPU (max abs diff {ret.get('err')})"
+
+
+@pytest.mark.timeout(600)
+def test_ulysses_sp2_bit_identical_to_single_gpu(lib):
+    _run("sp")
+
+
+@pytest.mark.timeout(600)
+def test_cfg_parallel_bit_identical_to_sequential(lib):
+    _run("cfg")
