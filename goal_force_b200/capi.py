@@ -30,6 +30,7 @@ SIGNATURES = {
     "gf_layernorm_bf16": [_p, _ll, _p, _ll, _i, _i, _f, _p, _p, _p, _p, _p],
     "gf_rmsnorm_rope_bf16": [_p, _ll, _i, _i, _p, _f, _p, _i, _p],
     "gf_qk_rmsnorm_rope_bf16": [_p, _ll, _i, _i, _p, _p, _f, _p, _i, _p],
+    "gf_attention_tuning": [_i, _i],
     "gf_attention_bf16": [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _f, _p],
     "gf_patch_gather_bf16": [_p, _i, _p, _i, _p, _ll, _i, _i, _i, _p],
     "gf_unpatchify_bf16": [_p, _ll, _p, _i, _i, _i, _i, _p],
@@ -212,6 +213,12 @@ def qk_rmsnorm_rope_(qkv: torch.Tensor, weight_q: torch.Tensor, weight_k: torch.
     _call("rmsnorm_rope", 8.0 * rows * d, load().gf_qk_rmsnorm_rope_bf16, qkv.data_ptr(), _ld(qkv), rows, d,
           weight_q.data_ptr(), weight_k.data_ptr(), eps, _ptr(cos_sin), head_dim, _stream())
     return qkv
+
+
+def attention_tuning(impl: int = 80, emu_pairs: int = 0) -> None:
+    """Select the attention kernel (80 = decoupled 80-row blocks, 128 = aliased 128-row blocks) and the share of
+    exponentials evaluated on the FMA pipe."""
+    _check(load().gf_attention_tuning(impl, emu_pairs), "gf_attention_tuning")
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, out: torch.Tensor | None = None,

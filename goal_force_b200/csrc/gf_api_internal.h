@@ -16,4 +16,9 @@ int gf_num_sms();
 int gf_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
                          uint32_t box_inner, uint32_t box_outer);
 
+// gf_attn80.cu: the decoupled 80-row-block attention kernel behind gf_attention_bf16 (arguments as the C ABI).
+int gf_attention80_launch(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                          void* O, long long ldo, int Lq, int Lk, int heads, float scale, int emu_pairs,
+                          cudaStream_t stream);
+
 }  // namespace gf

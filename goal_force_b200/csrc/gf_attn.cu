@@ -29,7 +29,7 @@
 //     exponentiated.
 #include <cstdlib>
 #include <type_traits>
-#include "gf_ptx.cuh"
+#include "gf_attn_common.cuh"
 #include "gf_api_internal.h"
 
 namespace gf {
@@ -53,84 +53,6 @@ struct AttnParams {
   int q_blocks;          // ceil(Lq / 256)
   float scale_log2;      // softmax scale * log2(e)
 };
-
-// ------------------------------------------------------------------ packed f32x2 helpers (FFMA2 / FADD2 on sm_100)
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
-
-// 2^x for two lanes on the FMA pipe: x = n + r, n = rint(x), r in [-0.5, 0.5];  2^r by a degree-3 minimax
-// polynomial (max relative error 7.5e-5), 2^n by adding n to the exponent field.  x is clamped to >= -125.
-__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
-  constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: low mantissa bits of (x + kMagic) hold rint(x)
-  float x0, x1;
-  unpack2(x2, x0, x1);
-  x0 = fmaxf(x0, -125.0f);
-  x1 = fmaxf(x1, -125.0f);
-  x2 = pack2(x0, x1);
-  const uint64_t t2 = fadd2(x2, pack2(kMagic, kMagic));
-  const uint64_t n2 = fadd2(t2, pack2(-kMagic, -kMagic));
-  const uint64_t r2 = ffma2(n2, pack2(-1.0f, -1.0f), x2);
-  uint64_t q2 = ffma2(pack2(0.0551716685295105f, 0.0551716685295105f), r2, pack2(0.2426111251115799f, 0.2426111251115799f));
-  q2 = ffma2(q2, r2, pack2(0.6932609677314758f, 0.6932609677314758f));
-  q2 = ffma2(q2, r2, pack2(0.9999280571937561f, 0.9999280571937561f));
-  float q0, q1, t0, t1;
-  unpack2(q2, q0, q1);
-  unpack2(t2, t0, t1);
-  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
-  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
-}
-
-// Exponentiate one 32-column chunk of a score row: p = 2^(s*scale - m), accumulate the row sum, pack to bf16.
-// kEmuPairs of the 16 column pairs go through the polynomial, spread evenly between the MUFU pairs.
-template <int kEmuPairs>
-__device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], uint64_t scale2, uint64_t negm2, uint64_t (&acc)[2],
-                                          uint32_t (&pk)[16]) {
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const uint64_t x2 = ffma2(pack2u(s[2 * k], s[2 * k + 1]), scale2, negm2);
-    float p0, p1;
-    const bool emulate = ((k + 1) * kEmuPairs) / 16 != (k * kEmuPairs) / 16;
-    if (emulate) {
-      exp2_poly2(x2, p0, p1);
-    } else {
-      float x0, x1;
-      unpack2(x2, x0, x1);
-      p0 = ex2_approx(x0);
-      p1 = ex2_approx(x1);
-    }
-    acc[k & 1] = fadd2(acc[k & 1], pack2(p0, p1));
-    pk[k] = pack_bf16x2(p0, p1);
-  }
-}
-
-__device__ __forceinline__ float chunk_max(const uint32_t (&s)[32]) {
-  float m = fmaxf(__uint_as_float(s[0]), __uint_as_float(s[1]));
-#pragma unroll
-  for (int k = 1; k < 16; ++k) m = fmax3(m, __uint_as_float(s[2 * k]), __uint_as_float(s[2 * k + 1]));
-  return m;
-}
 
 template <int kEmuPairs>
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -171,8 +93,8 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(s_full(i), 1);
-        mbar_init(p_half(i), 128);
-        mbar_init(p_full(i), 128);
+        mbar_init(p_half(i), 4);       // one arrive per softmax warp
+        mbar_init(p_full(i), 4);
         mbar_init(o_done(i), 1);
       }
       fence_mbar_init();
@@ -338,7 +260,8 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_half(i));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_half(i));
       {
         const uint64_t negm2 = pack2(-m_used, -m_used);
         exp_chunk<kEmuPairs>(s[2], scale2, negm2, acc, pk);
@@ -348,7 +271,8 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full(i));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(i));
       float a0, a1, a2, a3;
       unpack2(acc[0], a0, a1);
       unpack2(acc[1], a2, a3);
@@ -388,16 +312,26 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-// Fraction of exponentials evaluated on the FMA pipe, in column pairs per 16 (0, 2, 4, 5, 6).  Tuning knob:
-// GF_ATTN_EMU_PAIRS in the environment overrides the default (read once).
+// Kernel selection.  Defaults are what the benchmarks use; GF_ATTN_IMPL / GF_ATTN_EMU_PAIRS in the environment (read
+// once) or gf_attention_tuning() override them:
+//   impl      : 80 = gf_attn80.cu (decoupled, 80-row kv blocks, four softmax warpgroups; default),
+//               128 = this file (128-row kv blocks, P aliases S)
+//   emu_pairs : column pairs per 16 whose exponential runs on the FMA pipe instead of the MUFU (0, 2, 4, 6)
+static int g_attn_impl = -1, g_attn_emu = -1;
+static int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+static int attn_impl() {
+  if (g_attn_impl < 0) g_attn_impl = env_int("GF_ATTN_IMPL", 80) == 128 ? 128 : 80;
+  return g_attn_impl;
+}
 static int attn_emu_pairs() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = std::getenv("GF_ATTN_EMU_PAIRS");
-    v = e ? std::atoi(e) : 4;
-    if (v != 0 && v != 2 && v != 4 && v != 5 && v != 6) v = 4;
+  if (g_attn_emu < 0) {
+    const int v = env_int("GF_ATTN_EMU_PAIRS", attn_impl() == 80 ? 0 : 4);
+    g_attn_emu = (v == 0 || v == 2 || v == 4 || v == 6) ? v : 0;
   }
-  return v;
+  return g_attn_emu;
 }
 
 template <int kEmuPairs>
@@ -417,6 +351,14 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
 
 }  // namespace gf
 
+extern "C" int gf_attention_tuning(int impl, int emu_pairs) {
+  if ((impl != 80 && impl != 128) || (emu_pairs != 0 && emu_pairs != 2 && emu_pairs != 4 && emu_pairs != 6))
+    return GF_ERR_BAD_ARG;
+  gf::g_attn_impl = impl;
+  gf::g_attn_emu = emu_pairs;
+  return 0;
+}
+
 extern "C" int gf_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V,
                                  long long ldv, void* O, long long ldo, int Lq, int Lk, int heads, int head_dim,
                                  float scale, void* stream) {
@@ -424,6 +366,9 @@ extern "C" int gf_attention_bf16(const void* Q, long long ldq, const void* K, lo
   if (!Q || !K || !V || !O || Lq <= 0 || Lk <= 0 || heads <= 0) return GF_ERR_BAD_ARG;
   if (head_dim != AT_D) return GF_ERR_UNSUPPORTED;
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8) || (reinterpret_cast<uintptr_t>(O) & 15)) return GF_ERR_BAD_ARG;
+  if (attn_impl() == 80)
+    return gf_attention80_launch(Q, ldq, K, ldk, V, ldv, O, ldo, Lq, Lk, heads, scale, attn_emu_pairs(),
+                                 reinterpret_cast<cudaStream_t>(stream));
   CUtensorMap tmQ, tmK, tmV;
   int rc = gf_make_tmap_2d_bf16(&tmQ, Q, (uint64_t)heads * AT_D, (uint64_t)Lq, (uint64_t)ldq, 64, AT_BM);
   if (rc) return rc;
@@ -441,7 +386,6 @@ extern "C" int gf_attention_bf16(const void* Q, long long ldq, const void* K, lo
   switch (attn_emu_pairs()) {
     case 0: return launch_attn<0>(tmQ, tmK, tmV, p, s);
     case 2: return launch_attn<2>(tmQ, tmK, tmV, p, s);
-    case 5: return launch_attn<5>(tmQ, tmK, tmV, p, s);
     case 6: return launch_attn<6>(tmQ, tmK, tmV, p, s);
     default: return launch_attn<4>(tmQ, tmK, tmV, p, s);
   }

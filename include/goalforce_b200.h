@@ -72,6 +72,12 @@ int gf_qk_rmsnorm_rope_bf16(void* qkv, long long ld, int rows, int d, const void
 int gf_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
                       void* O, long long ldo, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
 
+/* Selects the attention kernel behind gf_attention_bf16 (process-wide; results agree to rounding):
+ *   impl 80  : decoupled kernel, 80-row kv blocks, S and P in separate TMEM columns, four softmax warpgroups (default)
+ *   impl 128 : 128-row kv blocks, P aliases S in TMEM, two softmax warpgroups
+ *   emu_pairs in {0, 2, 4, 6}: column pairs per 16 whose exp2 runs on the FMA pipe (polynomial) instead of the MUFU. */
+int gf_attention_tuning(int impl, int emu_pairs);
+
 /* Patch gather for the (1,2,2) Conv3d patch embedding (wan_video_dit.py:307-308,341-349; ControlNet
  * src/goal_force/wan_video_new.py:83,91-92).  Reads channels of up to two NCTHW tensors (the torch.cat([x, y]) at
  * src/goal_force/wan_video_new.py:1457-1458 is never materialised) and writes tokens

@@ -124,9 +124,18 @@ def _attn_ref(q, k, v, heads):
     return F.scaled_dot_product_attention(qh, kh, vh)[0].transpose(0, 1).reshape(Lq, heads * 128)
 
 
+@pytest.fixture(params=[(80, 0), (80, 4), (128, 4), (128, 0)], ids=lambda p: f"impl{p[0]}-emu{p[1]}")
+def attn_variant(capi, request):
+    """every attention kernel variant selectable through gf_attention_tuning; the default is restored afterwards"""
+    capi.attention_tuning(*request.param)
+    yield request.param
+    capi.attention_tuning(80, 0)
+
+
 @pytest.mark.parametrize("Lq,Lk,heads,amp", [(256, 128, 1, 1.0), (1, 7, 1, 1.0), (300, 200, 2, 1.0), (512, 1024, 3, 1.0),
-                                              (256, 512, 1, 4.0), (1000, 1333, 2, 2.0), (130, 512, 12, 1.0)])
-def test_attention(capi, Lq, Lk, heads, amp):
+                                              (256, 512, 1, 4.0), (1000, 1333, 2, 2.0), (130, 512, 12, 1.0),
+                                              (257, 81, 1, 1.0), (640, 41, 2, 1.0), (700, 80, 1, 1.0)])
+def test_attention(capi, attn_variant, Lq, Lk, heads, amp):
     torch.manual_seed(4)
     q = (torch.randn(Lq, heads * 128, device="cuda") * amp).bfloat16()
     k = (torch.randn(Lk, heads * 128, device="cuda") * amp).bfloat16()
@@ -134,7 +143,7 @@ def test_attention(capi, Lq, Lk, heads, amp):
     assert rel(capi.attention(q, k, v, heads), _attn_ref(q, k, v, heads)) < 5e-3
 
 
-def test_attention_rescale_path_and_strided_views(capi):
+def test_attention_rescale_path_and_strided_views(capi, attn_variant):
     # keys sorted by growing magnitude force the running max to jump by > 2^8 between kv blocks (lazy-rescale branch)
     torch.manual_seed(5)
     L, heads = 640, 2
@@ -146,7 +155,7 @@ def test_attention_rescale_path_and_strided_views(capi):
     assert rel(capi.attention(q, k, v, heads), _attn_ref(q, k, v, heads)) < 5e-3
 
 
-def test_attention_softmax_properties_at_full_length(capi):
+def test_attention_softmax_properties_at_full_length(capi, attn_variant):
     # size-independent properties at L = 32760 (config 2), 2 heads:
     #   constant V  -> O == V exactly representable (softmax rows sum to 1);  permuting the keys leaves O unchanged
     torch.manual_seed(6)

@@ -325,7 +325,7 @@ def g_attn_one():
     """accuracy + sustained timing of the attention kernel as configured by GF_ATTN_EMU_PAIRS (one process = one variant)"""
     import torch
     from goal_force_b200 import capi
-    res = {"emu_pairs": os.environ.get("GF_ATTN_EMU_PAIRS", "default")}
+    res = {"emu_pairs": os.environ.get("GF_ATTN_EMU_PAIRS", "default"), "impl": os.environ.get("GF_ATTN_IMPL", "default")}
     heads, d = 40, 5120
     torch.manual_seed(0)
     # accuracy: L = 4096, all heads, vs fp32 SDPA; plus a growing-magnitude case that forces the rescale branch
@@ -365,14 +365,15 @@ def g_attn_one():
 
 def g_attn_sweep():
     res = {}
-    for emu in os.environ.get("GF_ATTN_SWEEP", "0,2,4,5,6").split(","):
-        env = dict(os.environ, GF_ATTN_EMU_PAIRS=emu, PYTHONUNBUFFERED="1")
+    for var in os.environ.get("GF_ATTN_SWEEP", "80:0,128:4").split(","):
+        impl, emu = var.split(":")
+        env = dict(os.environ, GF_ATTN_IMPL=impl, GF_ATTN_EMU_PAIRS=emu, PYTHONUNBUFFERED="1")
         r = subprocess.run([sys.executable, __file__, "attn_one"], env=env, capture_output=True, text=True, timeout=280)
-        print(f"---- GF_ATTN_EMU_PAIRS={emu} rc={r.returncode}\n{r.stdout[-2500:]}{r.stderr[-1500:]}", flush=True)
+        print(f"---- GF_ATTN_IMPL={impl} GF_ATTN_EMU_PAIRS={emu} rc={r.returncode}\n{r.stdout[-2500:]}{r.stderr[-1500:]}", flush=True)
         try:
-            res[emu] = json.loads((OUT / "check_attn_one.json").read_text())
+            res[var] = json.loads((OUT / "check_attn_one.json").read_text())
         except Exception:  # noqa: BLE001
-            res[emu] = {"rc": r.returncode}
+            res[var] = {"rc": r.returncode}
     return res
 
 
