@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=40, help="trunk blocks (40 = A14B; fewer only for debugging)")
     ap.add_argument("--controlnet-layers", type=int, default=CONTROLNET_LAYERS)
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="Ulysses exchange at N > 1: fused peer-memory stores (default) or NCCL all-to-all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-kernel table to stderr")
@@ -174,7 +176,7 @@ def workload_config(args, n):
     return {"workload": "configs[1]: Wan2.2 I2V A14B high-noise expert, one denoise step (= one DiT forward), Goal "
                         "Force mode (10-block ControlNet, target-force control latents), 81x480x832 = 32760 tokens",
             "tokens": FRAMES_LAT * (H_LAT // 2) * (W_LAT // 2), "trunk_blocks": args.layers,
-            "controlnet_blocks": args.controlnet_layers, "parallelism": f"ulysses_sp{n}" if n > 1 else "single_gpu",
+            "controlnet_blocks": args.controlnet_layers, "parallelism": f"ulysses_sp{n}_{args.transport}" if n > 1 else "single_gpu",
             "l2": "per-step working set (35 GB of weights + 3 GB of activations) is far larger than the 126 MB L2; "
                   "no explicit flush"}
 
@@ -191,6 +193,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     from goal_force_b200 import capi
     from goal_force_b200.pipeline import ParallelContext, ParallelLayout
@@ -198,7 +202,8 @@ def run_ours(args):
     from goal_force_b200.wan_dit import (ControlNetB200, DiTConfig, WAN22_I2V_A14B, WanModelB200, model_fn_wan_video)
     capi.load()
     cfg = DiTConfig(**{**WAN22_I2V_A14B.__dict__, "num_layers": args.layers})
-    par = ParallelContext(ParallelLayout(world_size=world, rank=rank, cfg_size=1)) if world > 1 else None
+    par = (ParallelContext(ParallelLayout(world_size=world, rank=rank, cfg_size=1), transport=args.transport)
+           if world > 1 else None)
     sp = par.sp if par is not None else None
     dit = WanModelB200(cfg, LazyRandomStateDict(cfg, seed=0, device=dev), device=dev)
     cn = None

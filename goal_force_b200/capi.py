@@ -38,6 +38,16 @@ SIGNATURES = {
     "gf_silu_bf16": [_p, _p, _ll, _p],
     "gf_cfg_euler_bf16": [_p, _p, _p, _p, _f, _f, _ll, _p],
     "gf_timestep_embedding_bf16": [_p, _p, _i, _i, _p],
+    "gf_peer_alloc": [ctypes.POINTER(ctypes.c_void_p), _ll],
+    "gf_peer_free": [_p],
+    "gf_peer_export": [_p, _p],
+    "gf_peer_import": [_p, ctypes.POINTER(ctypes.c_void_p)],
+    "gf_peer_unimport": [_p],
+    "gf_peer_barrier": [ctypes.POINTER(ctypes.c_void_p), _i, _i, ctypes.c_uint, _p],
+    "gf_qkv_rmsnorm_rope_scatter_bf16": [_p, _ll, _i, _i, _p, _p, _f, _p, _i, ctypes.POINTER(ctypes.c_void_p), _i, _i,
+                                         _ll, _p],
+    "gf_attention_scatter_bf16": [_p, _ll, _p, _ll, _p, _ll, ctypes.POINTER(ctypes.c_void_p), _i, _ll, _i, _i, _i, _i,
+                                  _i, _i, _f, _p],
     "gf_ulysses_pack_bf16": [_p, _ll, _p, _ll, _i, _i, _i, _i, _p],
     "gf_ulysses_unpack_bf16": [_p, _p, _ll, _i, _i, _i, _i, _p],
 }
@@ -330,3 +340,84 @@ def ulysses_unpack(inp: torch.Tensor, rows: int, heads: int, head_dim: int, P: i
     _call("ulysses_pack", 4.0 * rows * heads * head_dim, load().gf_ulysses_unpack_bf16, inp.data_ptr(), out.data_ptr(),
           _ld(out), rows, heads, head_dim, P, _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ peer memory
+GF_PEER_HANDLE_BYTES = 64
+
+
+class _RawDeviceMemory:
+    """__cuda_array_interface__ shim: lets torch view a device buffer owned by the library (no copy)."""
+
+    def __init__(self, ptr: int, n_int16: int):
+        self.__cuda_array_interface__ = {"shape": (n_int16,), "typestr": "<i2", "data": (ptr, False), "version": 3}
+
+
+def peer_alloc(nbytes: int) -> int:
+    """Zero-filled device buffer that other processes on the node can map (gf_peer_alloc). Returns the pointer."""
+    out = ctypes.c_void_p()
+    _check(load().gf_peer_alloc(ctypes.byref(out), nbytes), "gf_peer_alloc")
+    return out.value
+
+
+def peer_free(ptr: int) -> None:
+    _check(load().gf_peer_free(ptr), "gf_peer_free")
+
+
+def peer_export(ptr: int) -> bytes:
+    buf = ctypes.create_string_buffer(GF_PEER_HANDLE_BYTES)
+    _check(load().gf_peer_export(ptr, buf), "gf_peer_export")
+    return buf.raw
+
+
+def peer_import(handle: bytes) -> int:
+    out = ctypes.c_void_p()
+    _check(load().gf_peer_import(handle, ctypes.byref(out)), "gf_peer_import")
+    return out.value
+
+
+def peer_unimport(ptr: int) -> None:
+    _check(load().gf_peer_unimport(ptr), "gf_peer_unimport")
+
+
+def as_bf16_tensor(ptr: int, shape, device) -> torch.Tensor:
+    """bf16 tensor view of library-owned device memory."""
+    n = 1
+    for s in shape:
+        n *= s
+    t = torch.as_tensor(_RawDeviceMemory(ptr, n), device=device)
+    return t.view(torch.bfloat16).view(*shape)
+
+
+def ptr_array(ptrs) -> ctypes.Array:
+    return (ctypes.c_void_p * len(ptrs))(*ptrs)
+
+
+def peer_barrier(flag_ptrs: ctypes.Array, n_peers: int, rank: int, epoch: int) -> None:
+    _call("peer_barrier", 0.0, load().gf_peer_barrier, flag_ptrs, n_peers, rank, epoch & 0xFFFFFFFF, _stream())
+
+
+def qkv_rmsnorm_rope_scatter(qkv: torch.Tensor, weight_q: torch.Tensor, weight_k: torch.Tensor, *, eps: float,
+                             cos_sin: torch.Tensor, head_dim: int, recv_ptrs: ctypes.Array, n_peers: int, rank: int,
+                             ld_recv: int) -> None:
+    """q/k RMSNorm + RoPE and v, stored straight into every head owner's receive buffer (Ulysses send, fused)."""
+    _req(qkv, "qkv"); _req(weight_q, "weight_q"); _req(weight_k, "weight_k"); _req(cos_sin, "cos_sin", torch.float32)
+    rows, d = qkv.shape[0], weight_q.numel()
+    if cos_sin.shape != (rows, head_dim // 2, 2) or not cos_sin.is_contiguous():
+        raise ValueError(f"cos_sin must be contiguous [rows, head_dim/2, 2], got {tuple(cos_sin.shape)}")
+    _call("rmsnorm_rope", 12.0 * rows * d, load().gf_qkv_rmsnorm_rope_scatter_bf16, qkv.data_ptr(), _ld(qkv), rows, d,
+          weight_q.data_ptr(), weight_k.data_ptr(), eps, cos_sin.data_ptr(), head_dim, recv_ptrs, n_peers, rank,
+          ld_recv, _stream())
+
+
+def attention_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, out_ptrs: ctypes.Array,
+                      n_peers: int, ldo: int, rows_per_peer: int, col_offset: int, scale: float | None = None) -> None:
+    """attention() whose output rows are stored into their owners' [rows_per_peer, ldo] buffers (Ulysses return)."""
+    _req(q, "q"); _req(k, "k"); _req(v, "v")
+    head_dim = 128
+    Lq, Lk = q.shape[0], k.shape[0]
+    if scale is None:
+        scale = head_dim ** -0.5
+    _call("attention_self", 4.0 * Lq * Lk * heads * head_dim, load().gf_attention_scatter_bf16, q.data_ptr(), _ld(q),
+          k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out_ptrs, n_peers, ldo, rows_per_peer, col_offset, Lq, Lk, heads,
+          head_dim, scale, _stream())

@@ -47,8 +47,7 @@ constexpr int AT_SMEM_BYTES = 2 * AT_TILE_BYTES + AT_SLOTS * AT_TILE_BYTES + 102
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;   // log2 domain
 
 struct AttnParams {
-  __nv_bfloat16* O;
-  long long ldo;
+  AttnOut out;
   int Lq, Lk, heads;
   int q_blocks;          // ceil(Lq / 256)
   float scale_log2;      // softmax scale * log2(e)
@@ -285,7 +284,14 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_wait(o_done(i), (n_kv - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l;
-    __nv_bfloat16* orow = p.O + (long long)row * p.ldo + col0;
+    __nv_bfloat16* orow;
+    if (p.out.n_peers == 0) {
+      orow = reinterpret_cast<__nv_bfloat16*>(p.out.base[0]) + (long long)row * p.out.ldo + col0;
+    } else {     // Ulysses return path: the row's owner receives it straight over NVLink
+      const int owner = min(row / p.out.rows_per_peer, p.out.n_peers - 1);
+      orow = reinterpret_cast<__nv_bfloat16*>(p.out.base[owner]) +
+             (long long)(row - owner * p.out.rows_per_peer) * p.out.ldo + p.out.col_offset + col0;
+    }
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t o[32];
@@ -359,16 +365,18 @@ extern "C" int gf_attention_tuning(int impl, int emu_pairs) {
   return 0;
 }
 
-extern "C" int gf_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V,
-                                 long long ldv, void* O, long long ldo, int Lq, int Lk, int heads, int head_dim,
-                                 float scale, void* stream) {
+static int attention_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                              const gf::AttnOut& out, int Lq, int Lk, int heads, int head_dim, float scale,
+                              void* stream) {
   using namespace gf;
-  if (!Q || !K || !V || !O || Lq <= 0 || Lk <= 0 || heads <= 0) return GF_ERR_BAD_ARG;
+  if (!Q || !K || !V || Lq <= 0 || Lk <= 0 || heads <= 0) return GF_ERR_BAD_ARG;
   if (head_dim != AT_D) return GF_ERR_UNSUPPORTED;
-  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8) || (reinterpret_cast<uintptr_t>(O) & 15)) return GF_ERR_BAD_ARG;
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (out.ldo % 8) || (out.col_offset % 8)) return GF_ERR_BAD_ARG;
+  for (int i = 0; i < (out.n_peers ? out.n_peers : 1); ++i)
+    if (!out.base[i] || (reinterpret_cast<uintptr_t>(out.base[i]) & 15)) return GF_ERR_BAD_ARG;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (attn_impl() == 80)
-    return gf_attention80_launch(Q, ldq, K, ldk, V, ldv, O, ldo, Lq, Lk, heads, scale, attn_emu_pairs(),
-                                 reinterpret_cast<cudaStream_t>(stream));
+    return gf_attention80_launch(Q, ldq, K, ldk, V, ldv, out, Lq, Lk, heads, scale, attn_emu_pairs(), s);
   CUtensorMap tmQ, tmK, tmV;
   int rc = gf_make_tmap_2d_bf16(&tmQ, Q, (uint64_t)heads * AT_D, (uint64_t)Lq, (uint64_t)ldq, 64, AT_BM);
   if (rc) return rc;
@@ -377,16 +385,38 @@ extern "C" int gf_attention_bf16(const void* Q, long long ldq, const void* K, lo
   rc = gf_make_tmap_2d_bf16(&tmV, V, (uint64_t)heads * AT_D, (uint64_t)Lk, (uint64_t)ldv, 64, AT_BN);
   if (rc) return rc;
   AttnParams p;
-  p.O = reinterpret_cast<__nv_bfloat16*>(O);
-  p.ldo = ldo;
+  p.out = out;
   p.Lq = Lq; p.Lk = Lk; p.heads = heads;
   p.q_blocks = (Lq + 2 * AT_BM - 1) / (2 * AT_BM);
   p.scale_log2 = scale * 1.4426950408889634f;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (attn_emu_pairs()) {
     case 0: return launch_attn<0>(tmQ, tmK, tmV, p, s);
     case 2: return launch_attn<2>(tmQ, tmK, tmV, p, s);
     case 6: return launch_attn<6>(tmQ, tmK, tmV, p, s);
     default: return launch_attn<4>(tmQ, tmK, tmV, p, s);
   }
+}
+
+extern "C" int gf_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V,
+                                 long long ldv, void* O, long long ldo, int Lq, int Lk, int heads, int head_dim,
+                                 float scale, void* stream) {
+  gf::AttnOut out{};
+  out.base[0] = O;
+  out.ldo = ldo;
+  return attention_dispatch(Q, ldq, K, ldk, V, ldv, out, Lq, Lk, heads, head_dim, scale, stream);
+}
+
+extern "C" int gf_attention_scatter_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V,
+                                         long long ldv, void* const* O_peers, int n_peers, long long ldo,
+                                         int rows_per_peer, int col_offset, int Lq, int Lk, int heads, int head_dim,
+                                         float scale, void* stream) {
+  if (!O_peers || n_peers < 1 || n_peers > GF_MAX_PEERS || rows_per_peer <= 0 || col_offset < 0) return GF_ERR_BAD_ARG;
+  if ((long long)rows_per_peer * n_peers < Lq) return GF_ERR_BAD_ARG;
+  gf::AttnOut out{};
+  for (int i = 0; i < n_peers; ++i) out.base[i] = O_peers[i];
+  out.ldo = ldo;
+  out.n_peers = n_peers;
+  out.rows_per_peer = rows_per_peer;
+  out.col_offset = col_offset;
+  return attention_dispatch(Q, ldq, K, ldk, V, ldv, out, Lq, Lk, heads, head_dim, scale, stream);
 }

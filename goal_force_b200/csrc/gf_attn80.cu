@@ -50,8 +50,7 @@ constexpr int A8_SMEM_BYTES = 2 * A8_Q_BYTES + A8_SLOTS * A8_SLOT_BYTES + A8_XCH
 constexpr float A8_RESCALE_THRESHOLD = 8.0f;    // log2 domain
 
 struct Attn80Params {
-  __nv_bfloat16* O;
-  long long ldo;
+  AttnOut out;
   int Lq, Lk, heads;
   int q_blocks;          // ceil(Lq / 256)
   float scale_log2;      // softmax scale * log2(e)
@@ -300,7 +299,14 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float inv_l = 1.0f / (l + exchange(l, n_kv));
     mbar_wait(p_free(i), (n_kv - 1) & 1);
     tc_fence_after();
-    __nv_bfloat16* orow = p.O + (long long)row * p.ldo + col0 + hf * 64;
+    __nv_bfloat16* orow;
+    if (p.out.n_peers == 0) {
+      orow = reinterpret_cast<__nv_bfloat16*>(p.out.base[0]) + (long long)row * p.out.ldo + col0 + hf * 64;
+    } else {     // Ulysses return path: the row's owner receives it straight over NVLink
+      const int owner = min(row / p.out.rows_per_peer, p.out.n_peers - 1);
+      orow = reinterpret_cast<__nv_bfloat16*>(p.out.base[owner]) +
+             (long long)(row - owner * p.out.rows_per_peer) * p.out.ldo + p.out.col_offset + col0 + hf * 64;
+    }
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
@@ -342,7 +348,7 @@ static int launch80(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtens
 }
 
 int gf_attention80_launch(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
-                          void* O, long long ldo, int Lq, int Lk, int heads, float scale, int emu_pairs,
+                          const AttnOut& out, int Lq, int Lk, int heads, float scale, int emu_pairs,
                           cudaStream_t stream) {
   CUtensorMap tmQ, tmK, tmV;
   int rc = gf_make_tmap_2d_bf16(&tmQ, Q, (uint64_t)heads * A8_D, (uint64_t)Lq, (uint64_t)ldq, 64, A8_BM);
@@ -352,8 +358,7 @@ int gf_attention80_launch(const void* Q, long long ldq, const void* K, long long
   rc = gf_make_tmap_2d_bf16(&tmV, V, (uint64_t)heads * A8_D, (uint64_t)Lk, (uint64_t)ldv, 64, A8_BN);
   if (rc) return rc;
   Attn80Params p;
-  p.O = reinterpret_cast<__nv_bfloat16*>(O);
-  p.ldo = ldo;
+  p.out = out;
   p.Lq = Lq; p.Lk = Lk; p.heads = heads;
   p.q_blocks = (Lq + 2 * A8_BM - 1) / (2 * A8_BM);
   p.scale_log2 = scale * 1.4426950408889634f;

@@ -176,6 +176,77 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, long long seg_
   }
 }
 
+// ---------------------------------------------------------------------------------------------- Ulysses scatter
+// Same math as rmsnorm_rope_kernel for q (segment 0) and k (segment 1), v (segment 2) is passed through; the result
+// is not written back but stored into the receive buffers of the ranks that own the heads: thread columns
+// [col, col + 8) of segment g belong to rank col / w (w = d / n_peers columns per rank, a multiple of 128) and land
+// there at row rank*rows + row, column g*w + col % w.  Remote stores are 16 bytes per thread, 512 contiguous bytes
+// per warp: NVLink-friendly.
+struct ScatterDst {
+  __nv_bfloat16* recv[GF_MAX_PEERS];
+  long long ld_recv;
+  int n_peers, rank;
+};
+
+template <int NVT, int TPR>
+__global__ void __launch_bounds__(ROW_THREADS)
+qkv_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int rows, float eps,
+                   const __nv_bfloat16* __restrict__ weight_q, const __nv_bfloat16* __restrict__ weight_k,
+                   const float* __restrict__ cos_sin, int half_dim, const ScatterDst dst) {
+  constexpr int d = NVT * TPR * 8;
+  constexpr int RPC = ROW_THREADS / TPR;
+  __shared__ float red[ROW_THREADS / 32];
+  const int t = threadIdx.x % TPR;
+  const int row = blockIdx.x * RPC + threadIdx.x / TPR;
+  const bool live = row < rows;
+  const int seg = blockIdx.y;
+  const __nv_bfloat16* xr = qkv + (long long)(live ? row : 0) * ld + (long long)seg * d;
+  uint4 v[NVT];
+#pragma unroll
+  for (int i = 0; i < NVT; ++i) v[i] = ld_stream(xr + (i * TPR + t) * 8);
+  float r = 1.0f;
+  if (seg < 2) {   // uniform per CTA: every thread reaches the barrier inside row_sum
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVT; ++i) {
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ss += bf16_lo(w[j]) * bf16_lo(w[j]) + bf16_hi(w[j]) * bf16_hi(w[j]);
+    }
+    r = rsqrtf(row_sum<TPR>(ss, red) * (1.0f / d) + eps);
+  }
+  if (!live) return;
+  const int w_cols = d / dst.n_peers;
+  const long long drow = (long long)dst.rank * rows + row;
+  float cs[4], sn[4];
+  if (seg < 2) {
+    const float4* tb = reinterpret_cast<const float4*>(cos_sin + ((long long)row * half_dim + (t * 4) % half_dim) * 2);
+    const float4 t0 = __ldg(tb), t1 = __ldg(tb + 1);
+    cs[0] = t0.x; sn[0] = t0.y; cs[1] = t0.z; sn[1] = t0.w;
+    cs[2] = t1.x; sn[2] = t1.y; cs[3] = t1.z; sn[3] = t1.w;
+  }
+  const __nv_bfloat16* weight = seg ? weight_k : weight_q;
+#pragma unroll
+  for (int i = 0; i < NVT; ++i) {
+    const int col = (i * TPR + t) * 8;
+    uint4 o = v[i];
+    if (seg < 2) {
+      const uint4 wv = __ldg(reinterpret_cast<const uint4*>(weight + col));
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      uint32_t oo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = round_bf16(round_bf16(bf16_lo(w[j]) * r) * bf16_lo(ww[j]));
+        const float b = round_bf16(round_bf16(bf16_hi(w[j]) * r) * bf16_hi(ww[j]));
+        oo[j] = pack_bf16x2(a * cs[j] - b * sn[j], a * sn[j] + b * cs[j]);
+      }
+      o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+    }
+    const int owner = col / w_cols;
+    *reinterpret_cast<uint4*>(dst.recv[owner] + drow * dst.ld_recv + seg * w_cols + (col - owner * w_cols)) = o;
+  }
+}
+
 template <int NVT, int TPR>
 static void launch_ln(cudaStream_t s, const __nv_bfloat16* X, long long ldx, __nv_bfloat16* Y, long long ldy, int rows,
                       float eps, const __nv_bfloat16* SH, const __nv_bfloat16* SC, const __nv_bfloat16* W,
@@ -246,4 +317,40 @@ extern "C" int gf_qk_rmsnorm_rope_bf16(void* qkv, long long ld, int rows, int d,
   return rms_dispatch(reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<__nv_bfloat16*>(qkv), ld, d, 2, rows, d,
                       eps, reinterpret_cast<const __nv_bfloat16*>(weight_q),
                       reinterpret_cast<const __nv_bfloat16*>(weight_k), cos_sin, head_dim / 2);
+}
+
+extern "C" int gf_qkv_rmsnorm_rope_scatter_bf16(const void* qkv, long long ld, int rows, int d, const void* weight_q,
+                                                const void* weight_k, float eps, const float* cos_sin, int head_dim,
+                                                void* const* recv_peers, int n_peers, int rank, long long ld_recv,
+                                                void* stream) {
+  using namespace gf;
+  if (!qkv || !weight_q || !weight_k || !cos_sin || !recv_peers || rows <= 0 || (ld % 8) || ld < 3LL * d)
+    return GF_ERR_BAD_ARG;
+  if (head_dim != 128) return GF_ERR_UNSUPPORTED;
+  if (n_peers < 1 || n_peers > GF_MAX_PEERS || rank < 0 || rank >= n_peers || d % (n_peers * 128) || (ld_recv % 8) ||
+      ld_recv < 3LL * (d / n_peers))
+    return GF_ERR_BAD_ARG;
+  ScatterDst dst{};
+  for (int i = 0; i < n_peers; ++i) {
+    if (!recv_peers[i] || (reinterpret_cast<uintptr_t>(recv_peers[i]) & 15)) return GF_ERR_BAD_ARG;
+    dst.recv[i] = reinterpret_cast<__nv_bfloat16*>(recv_peers[i]);
+  }
+  dst.ld_recv = ld_recv;
+  dst.n_peers = n_peers;
+  dst.rank = rank;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  auto X = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  auto WQ = reinterpret_cast<const __nv_bfloat16*>(weight_q), WK = reinterpret_cast<const __nv_bfloat16*>(weight_k);
+  switch (d) {
+    case 5120: qkv_scatter_kernel<5, 128><<<dim3((rows + 1) / 2, 3), ROW_THREADS, 0, s>>>(X, ld, rows, eps, WQ, WK,
+                                                                                          cos_sin, 64, dst); break;
+    case 1536: qkv_scatter_kernel<3, 64><<<dim3((rows + 3) / 4, 3), ROW_THREADS, 0, s>>>(X, ld, rows, eps, WQ, WK,
+                                                                                         cos_sin, 64, dst); break;
+    case 512: qkv_scatter_kernel<2, 32><<<dim3((rows + 7) / 8, 3), ROW_THREADS, 0, s>>>(X, ld, rows, eps, WQ, WK,
+                                                                                        cos_sin, 64, dst); break;
+    case 256: qkv_scatter_kernel<1, 32><<<dim3((rows + 7) / 8, 3), ROW_THREADS, 0, s>>>(X, ld, rows, eps, WQ, WK,
+                                                                                        cos_sin, 64, dst); break;
+    default: return GF_ERR_UNSUPPORTED;
+  }
+  return (int)cudaGetLastError();
 }

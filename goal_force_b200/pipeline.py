@@ -90,7 +90,7 @@ class ParallelLayout:
 class ParallelContext:
     """torch.distributed groups for a ParallelLayout (every rank must construct it: new_group is collective)."""
 
-    def __init__(self, layout: ParallelLayout):
+    def __init__(self, layout: ParallelLayout, transport: str = "peer"):
         import torch.distributed as dist
         self.dist = dist
         self.layout = layout
@@ -105,7 +105,7 @@ class ParallelContext:
                 g = dist.new_group(layout.cfg_ranks(s))
                 if s == layout.sp_index:
                     self.cfg_group = g
-        self.sp = SequenceParallel(self.sp_group) if layout.sp_size > 1 else None
+        self.sp = SequenceParallel(self.sp_group, transport=transport) if layout.sp_size > 1 else None
 
 
 class GoalForceDenoiser:

@@ -131,19 +131,76 @@ def _workspace(L: int, cfg: DiTConfig, device) -> _Workspace:
     return ws
 
 
+class PeerExchange:
+    """Peer-memory buffers of one rank for the fused Ulysses exchange (include/goalforce_b200.h, gf_peer_*):
+      recv [P*Ll, 3w]  q|k|v of this rank's heads for ALL tokens, written by every rank's RMSNorm+RoPE kernel
+      ao   [Ll, d]     attention output of ALL heads for this rank's tokens, written by every rank's attention kernel
+      flags            barrier slots
+    The buffers are allocated by the library (cudaMalloc) and mapped into the peers with CUDA IPC; the handles travel
+    through torch.distributed once per (token count, width)."""
+
+    def __init__(self, dist, group, rank: int, size: int, Ll: int, d: int, device):
+        if size > 8:
+            raise ValueError("peer exchange is limited to the 8 GPUs of one NVSwitch domain")
+        self.rank, self.size, self.Ll, self.d = rank, size, Ll, d
+        self.w = d // size
+        sizes = {"recv": size * Ll * 3 * self.w * 2, "ao": Ll * d * 2, "flags": 256}
+        self.local = {k: capi.peer_alloc(n) for k, n in sizes.items()}
+        mine = {k: capi.peer_export(p) for k, p in self.local.items()}
+        everyone = [None] * size
+        dist.all_gather_object(everyone, mine, group=group)
+        self._imported = []
+        ptrs = {k: [] for k in sizes}
+        for r in range(size):
+            for k in sizes:
+                if r == rank:
+                    ptrs[k].append(self.local[k])
+                else:
+                    p = capi.peer_import(everyone[r][k])
+                    self._imported.append(p)
+                    ptrs[k].append(p)
+        self.recv_ptrs, self.ao_ptrs, self.flag_ptrs = (capi.ptr_array(ptrs[k]) for k in ("recv", "ao", "flags"))
+        self.recv = capi.as_bf16_tensor(self.local["recv"], (size * Ll, 3 * self.w), device)
+        self.ao = capi.as_bf16_tensor(self.local["ao"], (Ll, d), device)
+        self.epoch = 0
+        dist.barrier(group=group)          # every rank has mapped every buffer before anybody writes
+
+    def barrier(self) -> None:
+        """All ranks' earlier kernels (on their compute streams) are complete and visible when this returns on the
+        stream; the only collective left in the exchange."""
+        self.epoch += 1
+        capi.peer_barrier(self.flag_ptrs, self.size, self.rank, self.epoch)
+
+    def close(self) -> None:
+        for p in self._imported:
+            capi.peer_unimport(p)
+        self._imported = []
+        for p in self.local.values():
+            capi.peer_free(p)
+        self.local = {}
+
+
 class SequenceParallel:
     """Ulysses sequence parallelism over one torch.distributed group (replaces
     diffsynth/distributed/xdit_context_parallel.py:42-131 and the xfuser dependency).
-    Tokens are split contiguously over ranks; per self-attention one all-to-all moves q,k,v from
-    [L/P, heads] to [L, heads/P] and one brings the output back."""
+    Tokens are split contiguously over ranks; per self-attention q,k,v move from [L/P, heads] to [L, heads/P] and the
+    output moves back.  Two transports:
+      "peer": fused -- the RMSNorm+RoPE kernel stores q|k|v directly into the head owners' buffers over NVLink and the
+              attention kernel stores its output rows directly into the token owners' buffers; two flag barriers per
+              attention replace the two all-to-alls (no pack / unpack kernels, no NCCL on the path);
+      "nccl": pack kernel -> all_to_all_single -> attention -> all_to_all_single -> unpack kernel (baseline)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, transport: str = "nccl"):
         import torch.distributed as dist
+        if transport not in ("peer", "nccl"):
+            raise ValueError("transport must be 'peer' or 'nccl'")
         self.dist = dist
         self.group = group
         self.size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.transport = transport
         self._bufs: dict = {}
+        self._peer: dict = {}
 
     def token_slice(self, L: int) -> slice:
         if L % self.size:
@@ -162,13 +219,26 @@ class SequenceParallel:
             self._bufs = {key: b}
         return b
 
+    def peer_exchange(self, Ll: int, d: int, device) -> PeerExchange:
+        key = (Ll, d, str(device))
+        ex = self._peer.get(key)
+        if ex is None:
+            for old in self._peer.values():
+                old.close()
+            ex = PeerExchange(self.dist, self.group, self.rank, self.size, Ll, d, device)
+            self._peer = {key: ex}
+        return ex
+
+    def _check_heads(self, heads: int) -> int:
+        if heads % self.size:
+            raise ValueError(f"{heads} heads do not divide over {self.size} ranks")
+        return heads // self.size
+
     def self_attention(self, qkv: torch.Tensor, heads: int, out: torch.Tensor) -> None:
-        """qkv: [L/P, 3*d] (q|k|v, already normed + roped) -> out [L/P, d]."""
+        """NCCL transport. qkv: [L/P, 3*d] (q|k|v, already normed + roped) -> out [L/P, d]."""
         P, Ll = self.size, qkv.shape[0]
         d = qkv.shape[1] // 3
-        hp = heads // P
-        if heads % P:
-            raise ValueError(f"{heads} heads do not divide over {P} ranks")
+        hp = self._check_heads(heads)
         send, recv, o_full, o_recv = self.buffers(Ll, d, qkv.device)
         w = hp * 128
         for s in range(3):
@@ -177,6 +247,24 @@ class SequenceParallel:
         capi.attention(recv[:, :w], recv[:, w:2 * w], recv[:, 2 * w:], hp, out=o_full)
         self.dist.all_to_all_single(o_recv, o_full.view(P, Ll, w), group=self.group)
         capi.ulysses_unpack(o_recv, Ll, heads, 128, P, out=out)
+
+    def self_attention_fused(self, qkv: torch.Tensor, norm_q: torch.Tensor, norm_k: torch.Tensor, eps: float,
+                             cos_sin: torch.Tensor, heads: int) -> torch.Tensor:
+        """Peer transport. qkv: [L/P, 3*d] straight out of the QKV GEMM (NOT yet normed). Returns the [L/P, d]
+        attention output (a view of the peer-visible buffer, valid until the next call)."""
+        P, Ll = self.size, qkv.shape[0]
+        d = qkv.shape[1] // 3
+        hp = self._check_heads(heads)
+        ex = self.peer_exchange(Ll, d, qkv.device)
+        w = ex.w
+        capi.qkv_rmsnorm_rope_scatter(qkv, norm_q, norm_k, eps=eps, cos_sin=cos_sin, head_dim=128,
+                                      recv_ptrs=ex.recv_ptrs, n_peers=P, rank=self.rank, ld_recv=3 * w)
+        ex.barrier()                                   # every rank's q|k|v has landed here
+        r = ex.recv
+        capi.attention_scatter(r[:, :w], r[:, w:2 * w], r[:, 2 * w:], hp, out_ptrs=ex.ao_ptrs, n_peers=P, ldo=d,
+                               rows_per_peer=Ll, col_offset=self.rank * w)
+        ex.barrier()                                   # every rank's heads have landed in my ao
+        return ex.ao
 
 
 def run_block(bw: _Block, cfg: DiTConfig, x: torch.Tensor, ctx_kv: torch.Tensor, mod: torch.Tensor,
@@ -190,12 +278,16 @@ def run_block(bw: _Block, cfg: DiTConfig, x: torch.Tensor, ctx_kv: torch.Tensor,
     # --- self attention
     capi.layernorm(x, eps=eps, shift=mod[0], scale=mod[1], out=h)
     capi.gemm(h, bw.wqkv, bw.bqkv, out=qkv)
-    capi.qk_rmsnorm_rope_(qkv, bw.norm_q, bw.norm_k, eps=eps, cos_sin=cos_sin, head_dim=128)
-    if sp is None or sp.size == 1:
-        capi.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], H, out=ao)
+    if sp is not None and sp.size > 1 and sp.transport == "peer":
+        attn = sp.self_attention_fused(qkv, bw.norm_q, bw.norm_k, eps, cos_sin, H)
     else:
-        sp.self_attention(qkv, H, ao)
-    capi.gemm(ao, bw.wo, bw.bo, epi=capi.GF_EPI_GATE_RES, gate=mod[2], residual=x, out=x)
+        capi.qk_rmsnorm_rope_(qkv, bw.norm_q, bw.norm_k, eps=eps, cos_sin=cos_sin, head_dim=128)
+        if sp is None or sp.size == 1:
+            capi.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], H, out=ao)
+        else:
+            sp.self_attention(qkv, H, ao)
+        attn = ao
+    capi.gemm(attn, bw.wo, bw.bo, epi=capi.GF_EPI_GATE_RES, gate=mod[2], residual=x, out=x)
     # --- cross attention
     capi.layernorm(x, eps=eps, weight=bw.n3w, bias=bw.n3b, out=h)
     capi.gemm(h, bw.cq_w, bw.cq_b, out=qc)

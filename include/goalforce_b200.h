@@ -25,6 +25,9 @@ extern "C" {
 #define GF_ERR_UNSUPPORTED (-4)  /* shape outside what the kernels are built for */
 
 /* GEMM epilogues (gf_gemm_bf16 `epi`) */
+#define GF_MAX_PEERS 8           /* GPUs of one NVSwitch domain that can take part in a peer exchange */
+#define GF_PEER_HANDLE_BYTES 64  /* size of an exported buffer handle (cudaIpcMemHandle_t) */
+
 #define GF_EPI_BIAS 0       /* C = A.W^T + bias                                                */
 #define GF_EPI_BIAS_GELU 1  /* C = gelu_tanh(A.W^T + bias)          wan_video_dit.py:209-210   */
 #define GF_EPI_BIAS_SILU 2  /* C = silu(A.W^T + bias)               wan_video_dit.py:314-318   */
@@ -117,6 +120,39 @@ int gf_ulysses_pack_bf16(const void* x, long long ldx, void* out, long long ldo,
                          int P, void* stream);
 int gf_ulysses_unpack_bf16(const void* in, void* y, long long ldy, int rows, int heads, int head_dim, int P,
                            void* stream);
+
+/* ---- fused Ulysses exchange over peer memory (NVLink / NVSwitch), one process per GPU --------------------------------
+ * Replaces the all-to-all pair around self-attention that the reference delegates to xfuser
+ * (diffsynth/distributed/xdit_context_parallel.py:110-131): the producing kernels store directly into the consumer
+ * GPU's buffers, and a flag barrier on the compute stream replaces the collective.
+ *
+ * gf_peer_alloc: zero-filled device buffer that other processes of the node may map (cudaMalloc + CUDA IPC).
+ * gf_peer_export / gf_peer_import: 64-byte handle of such a buffer / mapping of a peer's handle into this process
+ * (the host side exchanges the handles, e.g. with torch.distributed.all_gather_object).
+ * gf_peer_barrier: flag_peers[r] = rank r's flag buffer (>= 4*n_peers bytes, zero at start; own buffer at [rank]).
+ * Enqueues a kernel that publishes this rank's earlier writes, signals `epoch` to every peer and waits until every
+ * peer has signalled `epoch`; epochs must increase by one per call, identically on all ranks. */
+int gf_peer_alloc(void** ptr, long long bytes);
+int gf_peer_free(void* ptr);
+int gf_peer_export(void* ptr, void* handle64);
+int gf_peer_import(const void* handle64, void** ptr);
+int gf_peer_unimport(void* ptr);
+int gf_peer_barrier(void* const* flag_peers, int n_peers, int rank, unsigned epoch, void* stream);
+
+/* q/k RMSNorm + RoPE (as gf_qk_rmsnorm_rope_bf16) and v pass-through, written into the Ulysses receive buffers:
+ * rank p owns heads [p*heads/P, (p+1)*heads/P), w = heads/P*head_dim columns.  Row r of this rank (global token
+ * rank*rows + r) lands in recv_peers[p] at row rank*rows + r as [q_p | k_p | v_p] (3*w columns, pitch ld_recv).
+ * qkv itself is not modified.  recv_peers: host array of n_peers device pointers (own buffer at [rank]). */
+int gf_qkv_rmsnorm_rope_scatter_bf16(const void* qkv, long long ld, int rows, int d, const void* weight_q,
+                                     const void* weight_k, float eps, const float* cos_sin, int head_dim,
+                                     void* const* recv_peers, int n_peers, int rank, long long ld_recv, void* stream);
+
+/* gf_attention_bf16 whose output rows go back to their owners: global query row g belongs to rank g / rows_per_peer
+ * and is stored at O_peers[g / rows_per_peer] + (g % rows_per_peer)*ldo + col_offset + head*head_dim
+ * (col_offset = rank * heads * head_dim: this rank's head group inside the owner's [rows, all heads] buffer). */
+int gf_attention_scatter_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                              void* const* O_peers, int n_peers, long long ldo, int rows_per_peer, int col_offset,
+                              int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
 
 #ifdef __cplusplus
 }

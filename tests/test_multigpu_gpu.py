@@ -17,7 +17,7 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, mode, ret):
+def _worker(rank, world, port, mode, transport, ret):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -37,9 +37,11 @@ def _worker(rank, world, port, mode, ret):
         kw = dict(dit=dit, controlnet=cn, latents=inp["latents"], timestep=inp["timestep"], context=inp["context"],
                   y=inp["y"], control_signal_video_latents=inp["control_signal_video_latents"])
         if mode == "sp":
-            par = ParallelContext(ParallelLayout(world_size=world, rank=rank, cfg_size=1))
+            par = ParallelContext(ParallelLayout(world_size=world, rank=rank, cfg_size=1), transport=transport)
             single = model_fn_wan_video(**kw)
             multi = model_fn_wan_video(sequence_parallel=par.sp, **kw)
+            multi2 = model_fn_wan_video(sequence_parallel=par.sp, **kw)      # buffers / epochs reused
+            assert torch.equal(multi, multi2)
             ok = bool(torch.equal(single, multi))
             err = float((single.float() - multi.float()).abs().max())
         else:  # cfg axis: 2 ranks = conditional | unconditional
@@ -62,18 +64,19 @@ def _worker(rank, world, port, mode, ret):
         dist.destroy_process_group()
 
 
-def _run(mode):
+def _run(mode, transport="peer"):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), mode, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), mode, transport, ret), nprocs=2, join=True)
     assert ret.get("ok"), f"{mode}: multi-GPU result differs from single-GPU (max abs diff {ret.get('err')})"
 
 
 @pytest.mark.timeout(600)
-def test_ulysses_sp2_bit_identical_to_single_gpu(lib):
-    _run("sp")
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_ulysses_sp2_bit_identical_to_single_gpu(lib, transport):
+    _run("sp", transport)
 
 
 @pytest.mark.timeout(600)
