@@ -31,6 +31,7 @@ METRIC = "A14B DiT denoise steps/sec (81x480x832, 32760 tokens, goal-force Contr
 UNIT = "steps/s"
 FRAMES_LAT, H_LAT, W_LAT = 21, 60, 104          # 81 x 480 x 832 video -> latent grid; tokens = 21*30*52 = 32760
 CONTROLNET_LAYERS = 10
+ATTN_DRAM_BYTES_PER_LAUNCH = 1.044257e9 + 319.568384e6     # ncu: dram read + write of gf_attn80_kernel, L = 32760, 40 heads
 
 
 def parse():
@@ -281,9 +282,13 @@ def run_ours(args):
     roof = None
     if att["launches"]:
         ach = att["work"] / att["ms"] / 1e9
-        roof = {"kernel": "gf_attn_kernel (self-attention, tcgen05 flash attention)", "bound": "tensor",
+        roof = {"kernel": "gf_attn80_kernel (self-attention, tcgen05 flash attention)", "bound": "tensor",
                 "achieved": round(ach, 1), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops"], 4),
-                "peak_source": f"{pk['source']} (cuBLAS bf16 sustained, MEASURED_PEAKS.json)", "traffic": None,
+                "peak_source": f"{pk['source']} (cuBLAS bf16 sustained, MEASURED_PEAKS.json)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, from the ncu --set full
+                # capture summarised in profiles/r01_attn80_ncu.csv (algorithmic Q+K+V+O = 1.342e9 bytes)
+                "traffic": ATTN_DRAM_BYTES_PER_LAUNCH if (world == 1 and args.layers > 0) else None,
+                "traffic_unit": "bytes/launch (ncu, profiles/r01_attn80_ncu.csv)",
                 "launches": att["launches"], "avg_ms": round(att["ms"] / att["launches"], 4),
                 "share_of_step": round(att["ms"] / ms, 4),
                 "flops_per_launch": att["work"] / att["launches"]}
