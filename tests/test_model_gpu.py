@@ -112,9 +112,9 @@ def test_forward_controlnet_matches_reference_golden(golden_dir):
 
 
 def test_forward_config1_shape_vs_oracle():
-    """BASELINE.json configs[0]: Wan2.1-T2V-1.3B-shape DiT, one step at 17 frames 240x416 (L = 1950), here with 8 of
-    the 30 blocks to keep the fp32 oracle quick; the full 30-block run is tools/parity_report.py."""
-    cfg = O.DiTConfig(**{**O.WAN21_T2V_1_3B.__dict__, "num_layers": 8})
+    """BASELINE.json configs[0]: Wan2.1-T2V-1.3B-shape DiT (random init, all 30 blocks, dim 1536), one denoise step at
+    17 frames 240x416 (L = 1950), against the oracle in fp32 and bf16 on the same device."""
+    cfg = O.WAN21_T2V_1_3B
     sd = O.random_state_dict(cfg, seed=0)
     inp = O.synthetic_inputs(cfg, 5, 30, 52, seed=1, timestep=900.0)
     ref32, refbf = _oracle_pair(cfg, sd, inp)
