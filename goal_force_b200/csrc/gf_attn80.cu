@@ -52,7 +52,8 @@ constexpr float A8_RESCALE_THRESHOLD = 8.0f;    // log2 domain
 struct Attn80Params {
   AttnOut out;
   int Lq, Lk, heads;
-  int q_blocks;          // ceil(Lq / 256)
+  int q_blocks;          // ceil(Lq / 256): two-tile work items per head
+  int n_full;            // CTAs [0, n_full) take a whole two-tile item; CTAs beyond take ONE tile of a tail item each
   float scale_log2;      // softmax scale * log2(e)
 };
 
@@ -76,9 +77,16 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_ptr_smem = bar_base + 8u * (9 + 2 * A8_SLOTS);
 
   const int warp = threadIdx.x >> 5;
-  const int head = blockIdx.x / p.q_blocks;          // consecutive CTAs share a head's K/V in L2
-  const int qb = blockIdx.x % p.q_blocks;
-  const int q0 = qb * 2 * A8_BM;
+  // Work items are (head, 256 query rows).  When the last, partial wave of items would leave most SMs idle, the host
+  // splits those tail items into single-tile CTAs (`single`): tile 1's warps and issuer stay passive, and the tail
+  // wave runs on twice as many SMs at roughly 0.6x the per-block time.
+  const bool single = (int)blockIdx.x >= p.n_full;
+  const int tail_idx = single ? (int)blockIdx.x - p.n_full : 0;
+  const int item = single ? p.n_full + (tail_idx >> 1) : (int)blockIdx.x;
+  const int head = item / p.q_blocks;                // consecutive CTAs share a head's K/V in L2
+  const int qb = item % p.q_blocks;
+  const int q0 = qb * 2 * A8_BM + (tail_idx & 1) * A8_BM;
+  const int n_tiles = single ? 1 : 2;
   const int n_kv = (p.Lk + A8_BN - 1) / A8_BN;
   const int col0 = head * A8_D;
 
@@ -120,8 +128,8 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
    if (warp == 16) {
     // ===================================================== TMA producer: Q, K0, then K(j+1), V(j) for every block
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, 2 * A8_Q_BYTES);
-      for (int i = 0; i < 2; ++i)
+      mbar_arrive_expect_tx(q_full, n_tiles * A8_Q_BYTES);
+      for (int i = 0; i < n_tiles; ++i)
         for (int h = 0; h < 2; ++h)
           tma_load_2d(q_smem + i * A8_Q_BYTES + h * A8_QHALF, &tmQ, q_full, col0 + h * 64, q0 + i * A8_BM);
       int slot = 0;
@@ -141,7 +149,18 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
    } else if (warp == 17 || warp == 18) {
     // ===================================================== MMA issuers: warp 17 drives tile 0, warp 18 tile 1
-    if (elect_one()) {
+    if (warp == 18 && single) {
+      // passive tile: only keep the K/V ring turning (the slots are released by two arrivals)
+      if (elect_one()) {
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < 2 * n_kv; ++t) {
+          mbar_wait(kv_full(slot), phase);
+          mbar_arrive(kv_empty(slot));
+          if (++slot == A8_SLOTS) { slot = 0; phase ^= 1u; }
+        }
+      }
+    } else if (elect_one()) {
       const int i = warp - 17;
       constexpr uint32_t idesc_qk = idesc_bf16(A8_BM, A8_BN, 0, 0);   // A = Q (K-major), B = K (K-major), N = 80
       constexpr uint32_t idesc_pv = idesc_bf16(A8_BM, A8_D, 0, 1);    // A = P (TMEM),    B = V (MN-major), N = 128
@@ -192,7 +211,7 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
    }
-  } else {
+  } else if (!(single && warp >= 8)) {
     // ===================================================== softmax warpgroups (+ epilogue)
     setmaxnreg_inc<A8_SOFTMAX_REGS>();
     const int i = warp >> 3;                         // tile
@@ -343,7 +362,8 @@ static int launch80(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtens
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  kern<<<dim3(p.q_blocks * p.heads), dim3(A8_THREADS), A8_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  const int items = p.q_blocks * p.heads;
+  kern<<<dim3(p.n_full + 2 * (items - p.n_full)), dim3(A8_THREADS), A8_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   return (int)cudaGetLastError();
 }
 
@@ -361,6 +381,10 @@ int gf_attention80_launch(const void* Q, long long ldq, const void* K, long long
   p.out = out;
   p.Lq = Lq; p.Lk = Lk; p.heads = heads;
   p.q_blocks = (Lq + 2 * A8_BM - 1) / (2 * A8_BM);
+  // tail splitting: if the items of the last partial wave fit on the SMs as single-tile CTAs, run them that way
+  const int items = p.q_blocks * heads, sms = gf_num_sms();
+  const int tail = sms > 0 ? items % sms : 0;
+  p.n_full = (tail > 0 && items > sms && 2 * tail <= sms) ? items - tail : items;
   p.scale_log2 = scale * 1.4426950408889634f;
   switch (emu_pairs) {
     case 0: return launch80<0>(tmQ, tmK, tmV, p, stream);

@@ -134,7 +134,10 @@ def attn_variant(capi, request):
 
 @pytest.mark.parametrize("Lq,Lk,heads,amp", [(256, 128, 1, 1.0), (1, 7, 1, 1.0), (300, 200, 2, 1.0), (512, 1024, 3, 1.0),
                                               (256, 512, 1, 4.0), (1000, 1333, 2, 2.0), (130, 512, 12, 1.0),
-                                              (257, 81, 1, 1.0), (640, 41, 2, 1.0), (700, 80, 1, 1.0)])
+                                              (257, 81, 1, 1.0), (640, 41, 2, 1.0), (700, 80, 1, 1.0),
+                                              # 150 / 151 two-tile work items on 148 SMs: the tail items run as
+                                              # single-tile CTAs (gf_attn80.cu tail splitting)
+                                              (38400, 200, 1, 1.0), (38500, 333, 1, 1.0)])
 def test_attention(capi, attn_variant, Lq, Lk, heads, amp):
     torch.manual_seed(4)
     q = (torch.randn(Lq, heads * 128, device="cuda") * amp).bfloat16()

@@ -7,7 +7,8 @@ import torch
 from goal_force_b200 import capi
 
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 32760
-heads, d = 40, 5120
+heads = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+d = heads * 128
 qkv = torch.randn(L, 3 * d, device="cuda").bfloat16()
 o = torch.empty(L, d, device="cuda", dtype=torch.bfloat16)
 for _ in range(2):

@@ -354,6 +354,11 @@ def g_attn_one():
     idx = torch.randint(0, L, (48,), device="cuda")
     ref = _attn_ref(qkv[idx, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], heads)
     res["acc_L32760_rows"] = _stats(o[idx], ref)
+    # the 8-GPU Ulysses shape: 5 heads per rank, full sequence (640 work items on 148 SMs -> tail splitting)
+    h8 = 5
+    ms = timed(lambda: capi.attention(qkv[:, :h8 * 128], qkv[:, d:d + h8 * 128], qkv[:, 2 * d:2 * d + h8 * 128], h8,
+                                      out=o[:, :h8 * 128]), iters=10, warmup=2)
+    res["sp8_shape"] = {"ms": ms, "tflops": 4.0 * L * L * h8 * 128 / ms / 1e9}
     kv = torch.randn(512, 2 * d, device="cuda").bfloat16()
     q = qkv[:, :d].contiguous()
     ms = timed(lambda: capi.attention(q, kv[:, :d], kv[:, d:], heads, out=o), iters=20)
