@@ -223,3 +223,27 @@ def test_sampler_40_steps_two_experts_controlnet_cosine():
     cos = O.cosine(got, lat)
     print("40-step sampler cosine", cos, "relL2", O.rel_l2(got, lat))
     assert cos >= 0.999
+
+
+def test_models_from_safetensors_equal_models_from_state_dict(tmp_path):
+    """goal_force_b200.checkpoint: sharded expert + 'pipe.controlnet.'-prefixed ControlNet checkpoint give the same
+    forward, bit for bit, as the in-memory state dicts."""
+    from safetensors.torch import save_file
+    from goal_force_b200.checkpoint import load_controlnet, load_dit
+    from goal_force_b200.wan_dit import ControlNetB200, WanModelB200, model_fn_wan_video
+    cfg = O.DiTConfig(dim=256, in_dim=36, ffn_dim=512, out_dim=16, text_dim=64, freq_dim=256, eps=1e-6, num_heads=2,
+                      num_layers=2)
+    sd = {k: v.bfloat16().contiguous() for k, v in O.random_state_dict(cfg, seed=30).items()}
+    csd = {k: v.bfloat16().contiguous() for k, v in O.random_controlnet_state_dict(cfg, 1, seed=31).items()}
+    keys = sorted(sd)
+    save_file({k: sd[k] for k in keys[::2]}, str(tmp_path / "diffusion_pytorch_model-00001-of-00002.safetensors"))
+    save_file({k: sd[k] for k in keys[1::2]}, str(tmp_path / "diffusion_pytorch_model-00002-of-00002.safetensors"))
+    save_file({"pipe.controlnet." + k: v for k, v in csd.items()}, str(tmp_path / "step-3000.safetensors"))
+    pc = _prod_cfg(cfg)
+    dit_a, cn_a = WanModelB200(pc, sd), ControlNetB200(pc, csd, 1)
+    dit_b = load_dit(sorted(tmp_path.glob("diffusion_pytorch_model-*.safetensors")), pc)
+    cn_b = load_controlnet(tmp_path / "step-3000.safetensors", pc, 1)
+    inp = {k: v.to("cuda", torch.bfloat16) for k, v in O.synthetic_inputs(cfg, 2, 8, 12, seed=32, ctx_len=32, ctx_valid=8).items()}
+    kw = dict(latents=inp["latents"], timestep=inp["timestep"], context=inp["context"], y=inp["y"],
+              control_signal_video_latents=inp["control_signal_video_latents"])
+    assert torch.equal(model_fn_wan_video(dit=dit_a, controlnet=cn_a, **kw), model_fn_wan_video(dit=dit_b, controlnet=cn_b, **kw))
