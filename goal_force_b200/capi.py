@@ -54,7 +54,9 @@ SIGNATURES = {
 
 
 def lib_path() -> Path:
-    return Path(__file__).resolve().parent / "_lib" / "libgoalforce_b200.so"
+    """In-tree library; GF_B200_LIB points at another build of the SAME ABI (kernel A/B experiments)."""
+    override = os.environ.get("GF_B200_LIB")
+    return Path(override) if override else Path(__file__).resolve().parent / "_lib" / "libgoalforce_b200.so"
 
 
 def load() -> ctypes.CDLL:

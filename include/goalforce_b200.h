@@ -75,7 +75,9 @@ int gf_qk_rmsnorm_rope_bf16(void* qkv, long long ld, int rows, int d, const void
 int gf_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
                       void* O, long long ldo, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
 
-/* Selects the attention kernel behind gf_attention_bf16 (process-wide; results agree to rounding):
+/* Forces the attention kernel behind gf_attention_bf16 (process-wide; results agree to rounding).  Without this call
+ * (and without GF_ATTN_IMPL in the environment) the library picks per shape: impl 80 for long key sequences, impl 128
+ * for Lk <= 1024 (cross-attention).
  *   impl 80  : decoupled kernel, 80-row kv blocks, S and P in separate TMEM columns, four softmax warpgroups (default)
  *   impl 128 : 128-row kv blocks, P aliases S in TMEM, two softmax warpgroups
  *   emu_pairs in {0, 2, 4, 6}: column pairs per 16 whose exp2 runs on the FMA pipe (polynomial) instead of the MUFU. */

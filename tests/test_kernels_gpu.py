@@ -129,7 +129,7 @@ def attn_variant(capi, request):
     """every attention kernel variant selectable through gf_attention_tuning; the default is restored afterwards"""
     capi.attention_tuning(*request.param)
     yield request.param
-    capi.attention_tuning(80, 0)
+    capi.attention_tuning(80, 0)        # (a forced choice stays forced for the rest of the process; 80/0 is the default kernel)
 
 
 @pytest.mark.parametrize("Lq,Lk,heads,amp", [(256, 128, 1, 1.0), (1, 7, 1, 1.0), (300, 200, 2, 1.0), (512, 1024, 3, 1.0),

@@ -351,6 +351,25 @@ def g_attn_one():
     res["burst"] = {"ms": ms, "tflops": fl / ms / 1e9}
     ms = timed(run, iters=40, warmup=0)          # ~0.7 s back to back: settles under the power cap
     res["sustained"] = {"ms": ms, "tflops": fl / ms / 1e9}
+    # context: torch's own fused attention on this GPU (F.scaled_dot_product_attention; backend chosen by torch)
+    try:
+        import torch.nn.functional as F
+        q4, k4, v4 = (qkv[:, i * d:(i + 1) * d].reshape(1, L, heads, 128).transpose(1, 2) for i in range(3))
+        sd = lambda: F.scaled_dot_product_attention(q4, k4, v4)  # noqa: E731
+        ms = timed(sd, iters=3, warmup=1)
+        res["torch_sdpa_burst"] = {"ms": ms, "tflops": fl / ms / 1e9}
+        ms = timed(sd, iters=40, warmup=0)
+        res["torch_sdpa_sustained"] = {"ms": ms, "tflops": fl / ms / 1e9}
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        for name, be in (("cudnn", SDPBackend.CUDNN_ATTENTION), ("flash", SDPBackend.FLASH_ATTENTION)):
+            try:
+                with sdpa_kernel(be):
+                    ms = timed(sd, iters=3, warmup=1)
+                res[f"torch_sdpa_{name}"] = {"ms": ms, "tflops": fl / ms / 1e9}
+            except Exception as e:  # noqa: BLE001
+                res[f"torch_sdpa_{name}"] = {"error": repr(e)[:120]}
+    except Exception as e:  # noqa: BLE001
+        res["torch_sdpa_burst"] = {"error": repr(e)[:200]}
     idx = torch.randint(0, L, (48,), device="cuda")
     ref = _attn_ref(qkv[idx, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], heads)
     res["acc_L32760_rows"] = _stats(o[idx], ref)
