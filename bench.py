@@ -151,7 +151,7 @@ def cpu_reference_sample(threads: int):
     return 1.0 / t_step, t_tok + t_att, desc
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -170,7 +170,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def workload_config(args, n):
@@ -183,7 +183,7 @@ def workload_config(args, n):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def run_ours(args):
+def run_ours(args, emit):
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -194,8 +194,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner (and any debug output) to stdout; rank 0's stdout carries ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from goal_force_b200 import capi
     from goal_force_b200.pipeline import ParallelContext, ParallelLayout
@@ -321,17 +319,38 @@ def run_ours(args):
     if args.breakdown:
         for tag, ent in kernels.items():
             print(f"  {tag:16s} {ent}", file=sys.stderr)
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+class _StdoutToStderr:
+    """Rank 0's stdout must carry ONE JSON line, but NCCL prints its version banner (and libraries may print other
+    things) straight to file descriptor 1.  While active, fd 1 points at stderr; `emit` writes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text: str) -> None:
+        os.write(self._real, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._real, 1)
+        os.close(self._real)
+        return False
+
+
 def main():
     args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with _StdoutToStderr() as out:
+        if args.impl == "reference":
+            run_reference(args, out.emit)
+        else:
+            run_ours(args, out.emit)
 
 
 if __name__ == "__main__":
