@@ -127,8 +127,8 @@ def test_forward_config1_shape_vs_oracle():
 
 
 def test_a14b_width_two_blocks_long_sequence():
-    """A14B widths (d 5120, 40 heads, ffn 13824), 2 blocks + 1 ControlNet block, L = 4160 tokens (ragged tiles:
-    4160 = 32.5 x 128), against the oracle on the same device."""
+    """A14B widths (d 5120, 40 heads, ffn 13824), 2 blocks + 1 ControlNet block, L = 2080 tokens (ragged tiles:
+    2080 = 16.25 x 128 = 26 x 80), against the oracle on the same device."""
     cfg = O.DiTConfig(**{**O.WAN22_I2V_A14B.__dict__, "num_layers": 2})
     sd = O.random_state_dict(cfg, seed=2)
     csd = O.random_controlnet_state_dict(cfg, 1, seed=3)
