@@ -101,3 +101,27 @@ def test_rope_table_matches_oracle_freqs():
     assert torch.equal(cs[..., 0], fr.real.float()) and torch.equal(cs[..., 1], fr.imag.float())
     sl = slice(20, 40)
     assert torch.equal(rope_cos_sin(128, f, h, w, "cpu", sl), cs[sl])
+
+
+@pytest.mark.reference
+def test_model_fn_keyword_surface_matches_reference():
+    """Drop-in seam: every keyword the reference's model_fn_wan_video declares is accepted by ours with
+    the same default, so `pipe.model_fn = goal_force_b200.wan_dit.model_fn_wan_video` needs no call-site change."""
+    import inspect
+    from oracle import ref_shim
+    from goal_force_b200.wan_dit import model_fn_wan_video as ours
+    ref = ref_shim.load().model_fn_wan_video
+    rp, op = inspect.signature(ref).parameters, inspect.signature(ours).parameters
+    assert any(p.kind is inspect.Parameter.VAR_KEYWORD for p in op.values())      # shared-input junk is swallowed
+    for name, p in rp.items():
+        if p.kind is inspect.Parameter.VAR_KEYWORD:
+            continue
+        if name in op and p.default is not inspect.Parameter.empty:
+            assert op[name].default == p.default, name
+    # the names the pipeline always passes (in_iteration_models + inputs) are explicit parameters on our side
+    for name in ("dit", "controlnet", "latents", "timestep", "context", "y", "clip_feature"):
+        assert name in op and name in rp, name
+    wm_ref = inspect.signature(ref_shim.load().WanModel.forward).parameters
+    from goal_force_b200.wan_dit import WanModelB200
+    wm_ours = inspect.signature(WanModelB200.forward).parameters
+    assert [n for n in wm_ref if n not in ("self", "kwargs")] == [n for n in wm_ours if n not in ("self", "kwargs")]
