@@ -125,3 +125,33 @@ def test_model_fn_keyword_surface_matches_reference():
     from goal_force_b200.wan_dit import WanModelB200
     wm_ours = inspect.signature(WanModelB200.forward).parameters
     assert [n for n in wm_ref if n not in ("self", "kwargs")] == [n for n in wm_ours if n not in ("self", "kwargs")]
+
+
+@pytest.mark.reference
+def test_from_reference_modules_weight_layout():
+    """WanModelB200.from_reference / ControlNetB200.from_reference read the live reference nn.Modules: config taken
+    from the module attributes, q|k|v and cross k|v fused in the order the kernels expect, conv weights flattened with
+    K index c*4 + kh*2 + kw, an untouched (zero-conv) ControlNet recognised as a no-op."""
+    from oracle import ref_shim
+    from goal_force_b200.wan_dit import ControlNetB200, WanModelB200
+    ns = ref_shim.load()
+    cfg = O.DiTConfig(dim=256, in_dim=36, ffn_dim=512, out_dim=16, text_dim=64, freq_dim=256, eps=1e-6, num_heads=2,
+                      num_layers=2)
+    torch.manual_seed(0)
+    ref = ns.WanModel(**ref_shim.cfg_kwargs(cfg)).eval()
+    ours = WanModelB200.from_reference(ref, device="cpu")
+    c = ours.cfg
+    assert (c.dim, c.in_dim, c.ffn_dim, c.num_heads, c.num_layers, c.out_dim) == (256, 36, 512, 2, 2, 16)
+    sd = ref.state_dict()
+    b = ours.blocks[1]
+    want = torch.cat([sd[f"blocks.1.self_attn.{p}.weight"] for p in "qkv"], 0).bfloat16()
+    assert torch.equal(b.wqkv, want)
+    assert torch.equal(b.ckv_w, torch.cat([sd[f"blocks.1.cross_attn.{p}.weight"] for p in "kv"], 0).bfloat16())
+    assert torch.equal(ours.patch_w, sd["patch_embedding.weight"].reshape(256, 36 * 4).bfloat16())
+    assert torch.equal(ours.block_mod[0], sd["blocks.0.modulation"].reshape(-1).bfloat16())
+    # the goal-force ControlNet hard-codes A14B widths (SURVEY F7); one layer keeps this CPU-sized
+    cn_ref = ns.ControlNet(1, torch_dtype=torch.bfloat16)
+    cn = ControlNetB200.from_reference(cn_ref, device="cpu")
+    assert (cn.cfg.dim, cn.cfg.num_heads, cn.cfg.ffn_dim, cn.num_layers, cn.stride) == (5120, 40, 13824, 1, None)
+    assert cn.is_noop                                          # zero_module(...) convs: branch is an exact no-op
+    assert cn.patch_w.shape == (5120, 64) and cn.zero_w[0].shape == (5120, 5120)
