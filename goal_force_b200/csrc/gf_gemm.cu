@@ -19,6 +19,7 @@
 //   warps 2..5  : epilogue: tcgen05.ld accumulator -> registers -> fused math -> 16-byte global stores
 //   TMEM        : 2 accumulator stages x 256 fp32 columns (all 512 columns), so the epilogue of tile i overlaps the
 //                 MMAs of tile i+1.
+#include <cstdlib>
 #include "gf_ptx.cuh"
 #include "gf_api_internal.h"
 
@@ -29,7 +30,7 @@ constexpr int GEMM_BN = 256;       // columns per tile (per CTA, or per CTA pair
 constexpr int GEMM_BK = 64;        // bf16 elements per k-block == one 128-byte swizzle row
 constexpr int GEMM_UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_GROUP_M = 8;    // rasterisation: tiles walk 8 m-tiles before moving along N (L2 reuse of W)
+constexpr int GEMM_GROUP_M = 8;    // default rasterisation: tiles walk 8 m-tiles before moving along N (L2 reuse of W)
 
 template <int kCG> struct GemmCfg {
   static constexpr int kBRows = GEMM_BN / kCG;                           // W rows staged by each CTA
@@ -49,13 +50,14 @@ struct GemmParams {
   const __nv_bfloat16* R;         // [M, ldr] residual (EPI_GATE_RES), may alias C
   long long ldr;
   int num_m_tiles, num_n_tiles;   // in units of (128*kCG) x 256
+  int group_m;                    // rasterisation group height in m-tiles
 };
 
-__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m, int& n) {
-  const int per_group = GEMM_GROUP_M * num_n;
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int group_m, int& m, int& n) {
+  const int per_group = group_m * num_n;
   const int g = t / per_group;
-  const int first_m = g * GEMM_GROUP_M;
-  const int gsz = min(GEMM_GROUP_M, num_m - first_m);
+  const int first_m = g * group_m;
+  const int gsz = min(group_m, num_m - first_m);
   const int r = t - g * per_group;
   m = first_m + r % gsz;
   n = r / gsz;
@@ -128,7 +130,7 @@ gf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        int mt, nt; tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
+        int mt, nt; tile_coords(t, p.num_m_tiles, p.num_n_tiles, p.group_m, mt, nt);
         const int m0 = (mt * kCG + (int)cta_rank) * GEMM_BM;
         const int n0 = nt * GEMM_BN + (int)cta_rank * Cfg::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -181,7 +183,7 @@ gf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t lane = lane_id();
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      int mt, nt; tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
+      int mt, nt; tile_coords(t, p.num_m_tiles, p.num_n_tiles, p.group_m, mt, nt);
       const int row = (mt * kCG + (int)cta_rank) * GEMM_BM + q * 32 + (int)lane;
       const int n0 = nt * GEMM_BN;
       const bool row_ok = row < p.M;
@@ -319,6 +321,17 @@ extern "C" int gf_gemm_bf16(const void* A, long long lda, const void* W, long lo
   p.R = reinterpret_cast<const __nv_bfloat16*>(R); p.ldr = ldr;
   p.num_m_tiles = (M + GEMM_BM * cta_group - 1) / (GEMM_BM * cta_group);
   p.num_n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
+  {
+    // Rasterisation: tiles walk `group_m` m-tiles before moving along N.  Measured under sustained load at M = 32760
+    // (tools/gpu_check.py gemm_sustained): 16 is best for K = 5120 (each operand slab of a tile is 2.6 MB), 8 for
+    // K = 13824 (7 MB slabs: a taller group no longer fits L2 next to the W columns in flight); 4 and 32 lose 6-10 %.
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = std::getenv("GF_GEMM_GROUP_M");
+      forced = e ? std::atoi(e) : 0;
+    }
+    p.group_m = forced > 0 ? forced : (K <= 8192 ? 2 * GEMM_GROUP_M : GEMM_GROUP_M);
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return cta_group == 1 ? dispatch_epi<1>(epi, tmA, tmB, p, s) : dispatch_epi<2>(epi, tmA, tmB, p, s);
 }

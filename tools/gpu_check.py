@@ -260,6 +260,27 @@ def g_gemm_perf():
     return res
 
 
+def g_gemm_sustained():
+    """sustained (power-capped) GEMM rate at the four block shapes, for the rasterisation set by GF_GEMM_GROUP_M"""
+    import torch
+    from goal_force_b200 import capi
+    res = {"group_m": os.environ.get("GF_GEMM_GROUP_M", "default")}
+    M = 32760
+    tot_ms = 0.0
+    for (N, K) in [(15360, 5120), (5120, 5120), (13824, 5120), (5120, 13824)]:
+        a = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
+        b = torch.randn(N, device="cuda").bfloat16()
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ms = timed(lambda: capi.gemm(a, w, b, out=out), iters=150, warmup=10)
+        res[f"N{N}_K{K}"] = {"ms": round(ms, 4), "tflops": round(2.0 * M * N * K / ms / 1e9, 1)}
+        tot_ms += ms
+        del a, w, out
+    res["sum_ms"] = round(tot_ms, 4)
+    print(res, flush=True)
+    return res
+
+
 def g_attn_perf():
     import torch
     from goal_force_b200 import capi
@@ -405,6 +426,7 @@ GROUPS = {
     "gemm_small": g_gemm_small, "gemm_small2": g_gemm_small2, "gemm_epi": g_gemm_epi, "rowwise": g_rowwise,
     "misc": g_misc, "attn_small": g_attn_small, "gemm_perf": g_gemm_perf, "attn_perf": g_attn_perf,
     "rowwise_perf": g_rowwise_perf, "attn_one": g_attn_one, "attn_sweep": g_attn_sweep,
+    "gemm_sustained": g_gemm_sustained,
 }
 
 
