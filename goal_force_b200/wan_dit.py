@@ -520,6 +520,18 @@ class ControlNetB200:
 
 
 _CONVERTED: dict = {}
+_DEFAULT_SP: list = []
+
+
+def _default_sequence_parallel() -> "SequenceParallel | None":
+    """`use_unified_sequence_parallel=True` without an explicit SequenceParallel object (what the reference pipeline
+    passes after enable_usp, diffsynth/pipelines/wan_video_new.py:298-310): shard over the default process group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    if not _DEFAULT_SP:
+        _DEFAULT_SP.append(SequenceParallel(None, transport="peer"))
+    return _DEFAULT_SP[0]
 
 
 def _as_b200(obj, kind):
@@ -566,6 +578,8 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
     if clip_feature is not None and dit.require_clip_embedding:
         raise NotImplementedError("clip_feature branch (has_image_input) is not part of the A14B hot path")
     cfg = dit.cfg
+    if sequence_parallel is None and use_unified_sequence_parallel:
+        sequence_parallel = _default_sequence_parallel()
     sp = sequence_parallel if (sequence_parallel is not None and sequence_parallel.size > 1) else None
 
     B = max(latents.shape[0], context.shape[0])            # merged-CFG batches replicate latents (:1451-1454)

@@ -42,6 +42,8 @@ def _worker(rank, world, port, mode, transport, ret):
             multi = model_fn_wan_video(sequence_parallel=par.sp, **kw)
             multi2 = model_fn_wan_video(sequence_parallel=par.sp, **kw)      # buffers / epochs reused
             assert torch.equal(multi, multi2)
+            if transport == "peer":    # the reference's flag alone shards over the default group
+                assert torch.equal(model_fn_wan_video(use_unified_sequence_parallel=True, **kw), multi)
             ok = bool(torch.equal(single, multi))
             err = float((single.float() - multi.float()).abs().max())
         else:  # cfg axis: 2 ranks = conditional | unconditional
