@@ -98,19 +98,34 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat
         o[j] = pack_bf16x2((bf16_lo(w[j]) - mean) * rstd * bf16_lo(ww[j]) + bf16_lo(bw[j]),
                            (bf16_hi(w[j]) - mean) * rstd * bf16_hi(ww[j]) + bf16_hi(bw[j]));
     } else {
+      // bf16(bf16(LN) * bf16(1 + scale)) + shift with packed bf16x2 arithmetic: HADD2 / HMUL2 on bf16 compute in
+      // fp32 and round once, which is exactly what eager PyTorch does for each of these bf16 tensor ops (the _rn forms
+      // keep the compiler from contracting the multiply and the add into one fused, singly rounded HFMA2)
       const uint4 sc = __ldg(reinterpret_cast<const uint4*>(scale + col));
       const uint4 sh = __ldg(reinterpret_cast<const uint4*>(shift + col));
       const uint32_t cw[4] = {sc.x, sc.y, sc.z, sc.w}, hw[4] = {sh.x, sh.y, sh.z, sh.w};
+      const __nv_bfloat162 one2 = __floats2bfloat162_rn(1.0f, 1.0f);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float n0 = round_bf16((bf16_lo(w[j]) - mean) * rstd), n1 = round_bf16((bf16_hi(w[j]) - mean) * rstd);
-        const float m0 = round_bf16(n0 * round_bf16(1.0f + bf16_lo(cw[j])));
-        const float m1 = round_bf16(n1 * round_bf16(1.0f + bf16_hi(cw[j])));
-        o[j] = pack_bf16x2(m0 + bf16_lo(hw[j]), m1 + bf16_hi(hw[j]));
+        const __nv_bfloat162 n2 = __floats2bfloat162_rn((bf16_lo(w[j]) - mean) * rstd, (bf16_hi(w[j]) - mean) * rstd);
+        const __nv_bfloat162 s1p = __hadd2_rn(one2, *reinterpret_cast<const __nv_bfloat162*>(&cw[j]));
+        const __nv_bfloat162 r2 = __hadd2_rn(__hmul2_rn(n2, s1p), *reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
+        o[j] = *reinterpret_cast<const uint32_t*>(&r2);
       }
     }
     *reinterpret_cast<uint4*>(yr + col) = make_uint4(o[0], o[1], o[2], o[3]);
   }
+}
+
+// (a, b) = bf16( bf16(x * r) * weight ) for one packed pair, as fp32 values: the normalised pair is rounded to bf16
+// once (F2FP), the multiply by the bf16 weight is one HMUL2.BF16 (fp32 product, one rounding) -- the two roundings of
+// RMSNorm.forward (wan_video_dit.py:106-111) in eager PyTorch.
+__device__ __forceinline__ void rms_scale_pair(uint32_t x2, float r, uint32_t w2, float& a, float& b) {
+  const __nv_bfloat162 n2 = __floats2bfloat162_rn(bf16_lo(x2) * r, bf16_hi(x2) * r);
+  const __nv_bfloat162 m2 = __hmul2_rn(n2, *reinterpret_cast<const __nv_bfloat162*>(&w2));
+  const uint32_t m = *reinterpret_cast<const uint32_t*>(&m2);
+  a = bf16_lo(m);
+  b = bf16_hi(m);
 }
 
 // ---------------------------------------------------------------------------------------------- RMSNorm + RoPE
@@ -163,8 +178,8 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, long long seg_
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float a = round_bf16(round_bf16(bf16_lo(w[j]) * r) * bf16_lo(ww[j]));
-      float b = round_bf16(round_bf16(bf16_hi(w[j]) * r) * bf16_hi(ww[j]));
+      float a, b;
+      rms_scale_pair(w[j], r, ww[j], a, b);
       if (cos_sin) {
         const float ra = a * cs[j] - b * sn[j];
         const float rb = a * sn[j] + b * cs[j];
@@ -236,8 +251,8 @@ qkv_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int rows
       uint32_t oo[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float a = round_bf16(round_bf16(bf16_lo(w[j]) * r) * bf16_lo(ww[j]));
-        const float b = round_bf16(round_bf16(bf16_hi(w[j]) * r) * bf16_hi(ww[j]));
+        float a, b;
+        rms_scale_pair(w[j], r, ww[j], a, b);
         oo[j] = pack_bf16x2(a * cs[j] - b * sn[j], a * sn[j] + b * cs[j]);
       }
       o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
