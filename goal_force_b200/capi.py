@@ -19,6 +19,8 @@ GF_EPI_BIAS_GELU = 1
 GF_EPI_BIAS_SILU = 2
 GF_EPI_GATE_RES = 3
 
+ABI_VERSION = 2
+
 _ERRORS = {-1: "GF_ERR_BAD_ARG", -2: "GF_ERR_NO_DRIVER", -3: "GF_ERR_TMAP", -4: "GF_ERR_UNSUPPORTED"}
 
 # name -> argtypes; every entry point returns int
@@ -26,15 +28,20 @@ _p, _ll, _i, _f = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_flo
 SIGNATURES = {
     "gf_abi_version": [],
     "gf_device_sms": [],
-    "gf_gemm_bf16": [_p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p, _i, _p, _p, _ll, _i, _p],
+    "gf_ctx_create": [ctypes.POINTER(ctypes.c_void_p)],
+    "gf_ctx_destroy": [_p],
+    "gf_ctx_set_attention": [_p, _i, _i],
+    "gf_ctx_set_gemm_raster": [_p, _i],
+    "gf_ctx_stats": [_p, ctypes.POINTER(_ll), ctypes.POINTER(_ll), ctypes.POINTER(_ll)],
+    "gf_gemm_bf16": [_p, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p, _i, _p, _p, _ll, _i, _p],
     "gf_layernorm_bf16": [_p, _ll, _p, _ll, _i, _i, _f, _p, _p, _p, _p, _p],
     "gf_rmsnorm_rope_bf16": [_p, _ll, _i, _i, _p, _f, _p, _i, _p],
     "gf_qk_rmsnorm_rope_bf16": [_p, _ll, _i, _i, _p, _p, _f, _p, _i, _p],
-    "gf_attention_tuning": [_i, _i],
-    "gf_attention_bf16": [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _f, _p],
+    "gf_attention_bf16": [_p, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _f, _p],
     "gf_patch_gather_bf16": [_p, _i, _p, _i, _p, _ll, _i, _i, _i, _p],
     "gf_unpatchify_bf16": [_p, _ll, _p, _i, _i, _i, _i, _p],
     "gf_add_rows_bf16": [_p, _p, _p, _i, _i, _p],
+    "gf_add_bf16": [_p, _p, _p, _ll, _p],
     "gf_silu_bf16": [_p, _p, _ll, _p],
     "gf_cfg_euler_bf16": [_p, _p, _p, _p, _f, _f, _ll, _p],
     "gf_timestep_embedding_bf16": [_p, _p, _i, _i, _p],
@@ -43,11 +50,13 @@ SIGNATURES = {
     "gf_peer_export": [_p, _p],
     "gf_peer_import": [_p, ctypes.POINTER(ctypes.c_void_p)],
     "gf_peer_unimport": [_p],
-    "gf_peer_barrier": [ctypes.POINTER(ctypes.c_void_p), _i, _i, ctypes.c_uint, _p],
+    "gf_peer_barrier": [ctypes.POINTER(ctypes.c_void_p), _i, _i, _ll, _p, _p],
+    "gf_peer_status_alloc": [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)],
+    "gf_peer_status_free": [_p],
     "gf_qkv_rmsnorm_rope_scatter_bf16": [_p, _ll, _i, _i, _p, _p, _f, _p, _i, ctypes.POINTER(ctypes.c_void_p), _i, _i,
                                          _ll, _p],
-    "gf_attention_scatter_bf16": [_p, _ll, _p, _ll, _p, _ll, ctypes.POINTER(ctypes.c_void_p), _i, _ll, _i, _i, _i, _i,
-                                  _i, _i, _f, _p],
+    "gf_attention_scatter_bf16": [_p, _p, _ll, _p, _ll, _p, _ll, ctypes.POINTER(ctypes.c_void_p), _i, _ll, _i, _i, _i,
+                                  _i, _i, _i, _f, _p],
     "gf_ulysses_pack_bf16": [_p, _ll, _p, _ll, _i, _i, _i, _i, _p],
     "gf_ulysses_unpack_bf16": [_p, _p, _ll, _i, _i, _i, _i, _p],
 }
@@ -78,10 +87,40 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # raises AttributeError if a declared symbol is not exported
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int
-    if lib.gf_abi_version() != 1:
+    if lib.gf_abi_version() != ABI_VERSION:
         raise RuntimeError("libgoalforce_b200.so ABI version mismatch")
     _LIB = lib
     return lib
+
+
+_CTX: dict = {}
+
+
+def ctx() -> int:
+    """The gf_ctx of this process for the current CUDA device (descriptor cache + tuning), created on first use.
+    Initial tuning comes from the environment, read HERE once and never on the launch path:
+    GF_ATTN_IMPL (80 | 128), GF_ATTN_EMU_PAIRS (0 | 2 | 4 | 6), GF_GEMM_GROUP_M."""
+    dev = torch.cuda.current_device()
+    c = _CTX.get(dev)
+    if c is None:
+        out = ctypes.c_void_p()
+        _check(load().gf_ctx_create(ctypes.byref(out)), "gf_ctx_create")
+        c = out.value
+        _CTX[dev] = c
+        impl = int(os.environ.get("GF_ATTN_IMPL", "0"))
+        emu = int(os.environ.get("GF_ATTN_EMU_PAIRS", "-1"))
+        if impl or emu >= 0:
+            _check(load().gf_ctx_set_attention(c, impl, emu), "gf_ctx_set_attention")
+        gm = int(os.environ.get("GF_GEMM_GROUP_M", "0"))
+        if gm:
+            _check(load().gf_ctx_set_gemm_raster(c, gm), "gf_ctx_set_gemm_raster")
+    return c
+
+
+def ctx_stats() -> dict:
+    e, h, m = _ll(), _ll(), _ll()
+    _check(load().gf_ctx_stats(ctx(), ctypes.byref(e), ctypes.byref(h), ctypes.byref(m)), "gf_ctx_stats")
+    return {"tmap_entries": e.value, "tmap_hits": h.value, "tmap_misses": m.value}
 
 
 def _check(rc: int, what: str) -> None:
@@ -175,7 +214,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, 
         _req(residual, "residual")
         if gate is not None:
             _req(gate, "gate")
-    _call("gemm", 2.0 * M * N * K, load().gf_gemm_bf16, a.data_ptr(), _ld(a), w.data_ptr(), _ld(w), out.data_ptr(),
+    _call("gemm", 2.0 * M * N * K, load().gf_gemm_bf16, ctx(), a.data_ptr(), _ld(a), w.data_ptr(), _ld(w), out.data_ptr(),
           _ld(out), M, N, K, _ptr(bias), epi, _ptr(gate), _ptr(residual),
           _ld(residual) if residual is not None else 0, cta_group, _stream())
     return out
@@ -227,10 +266,14 @@ def qk_rmsnorm_rope_(qkv: torch.Tensor, weight_q: torch.Tensor, weight_k: torch.
     return qkv
 
 
-def attention_tuning(impl: int = 80, emu_pairs: int = 0) -> None:
-    """Select the attention kernel (80 = decoupled 80-row blocks, 128 = aliased 128-row blocks) and the share of
-    exponentials evaluated on the FMA pipe."""
-    _check(load().gf_attention_tuning(impl, emu_pairs), "gf_attention_tuning")
+def attention_tuning(impl: int = 0, emu_pairs: int = -1) -> None:
+    """Select the attention kernel of this process's context (0 = per shape, 80 = decoupled 80-row blocks,
+    128 = aliased 128-row blocks) and the share of exponentials evaluated on the FMA pipe (-1 = kernel default)."""
+    _check(load().gf_ctx_set_attention(ctx(), impl, emu_pairs), "gf_ctx_set_attention")
+
+
+def gemm_tuning(group_m: int = 0) -> None:
+    _check(load().gf_ctx_set_gemm_raster(ctx(), group_m), "gf_ctx_set_gemm_raster")
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, out: torch.Tensor | None = None,
@@ -244,7 +287,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, 
     if scale is None:
         scale = head_dim ** -0.5
     _call("attention_self" if Lk >= Lq else "attention_cross", 4.0 * Lq * Lk * heads * head_dim,
-          load().gf_attention_bf16, q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(),
+          load().gf_attention_bf16, ctx(), q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(),
           _ld(out), Lq, Lk, heads, head_dim, scale, _stream())
     return out
 
@@ -286,6 +329,16 @@ def add_rows(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) 
     _call("elementwise", 4.0 * a2.numel(), load().gf_add_rows_bf16, a2.data_ptr(), b.data_ptr(), out.data_ptr(),
           a2.shape[0], a2.shape[1], _stream())
     return out.view(a.shape)
+
+
+def add_(x: torch.Tensor, other: torch.Tensor) -> torch.Tensor:
+    """x += other (same shape, contiguous), one bf16 rounding per element like torch's bf16 add."""
+    _req(x, "x"); _req(other, "other")
+    if x.shape != other.shape or not x.is_contiguous() or not other.is_contiguous():
+        raise ValueError("add_ needs two contiguous tensors of the same shape")
+    _call("elementwise", 6.0 * x.numel(), load().gf_add_bf16, x.data_ptr(), other.data_ptr(), x.data_ptr(), x.numel(),
+          _stream())
+    return x
 
 
 def silu(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -395,8 +448,35 @@ def ptr_array(ptrs) -> ctypes.Array:
     return (ctypes.c_void_p * len(ptrs))(*ptrs)
 
 
-def peer_barrier(flag_ptrs: ctypes.Array, n_peers: int, rank: int, epoch: int) -> None:
-    _call("peer_barrier", 0.0, load().gf_peer_barrier, flag_ptrs, n_peers, rank, epoch & 0xFFFFFFFF, _stream())
+class PeerStatus:
+    """Host-mapped status word written by gf_peer_barrier when a peer does not arrive in time (gf_peer_status_alloc).
+    `check()` reads it from the CPU without synchronising the stream."""
+
+    def __init__(self):
+        h, d = ctypes.c_void_p(), ctypes.c_void_p()
+        _check(load().gf_peer_status_alloc(ctypes.byref(h), ctypes.byref(d)), "gf_peer_status_alloc")
+        self.host, self.dev = h.value, d.value
+        self._word = ctypes.cast(self.host, ctypes.POINTER(ctypes.c_uint))
+
+    def value(self) -> int:
+        return int(self._word[0]) if self.host else 0
+
+    def check(self, what: str = "gf_peer_barrier") -> None:
+        v = self.value()
+        if v:
+            raise RuntimeError(f"{what}: peer rank {v - 1} of the sequence-parallel group did not reach the barrier "
+                               f"within the timeout (GF_PEER_TIMEOUT_MS); results since then are invalid")
+
+    def free(self) -> None:
+        if self.host:
+            load().gf_peer_status_free(self.host)
+            self.host = self.dev = None
+
+
+def peer_barrier(flag_ptrs: ctypes.Array, n_peers: int, rank: int, timeout_ms: int = 0,
+                 status: PeerStatus | None = None) -> None:
+    _call("peer_barrier", 0.0, load().gf_peer_barrier, flag_ptrs, n_peers, rank, timeout_ms,
+          status.dev if status is not None else None, _stream())
 
 
 def qkv_rmsnorm_rope_scatter(qkv: torch.Tensor, weight_q: torch.Tensor, weight_k: torch.Tensor, *, eps: float,
@@ -420,6 +500,7 @@ def attention_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: 
     Lq, Lk = q.shape[0], k.shape[0]
     if scale is None:
         scale = head_dim ** -0.5
-    _call("attention_self", 4.0 * Lq * Lk * heads * head_dim, load().gf_attention_scatter_bf16, q.data_ptr(), _ld(q),
+    _call("attention_self", 4.0 * Lq * Lk * heads * head_dim, load().gf_attention_scatter_bf16, ctx(), q.data_ptr(),
+          _ld(q),
           k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out_ptrs, n_peers, ldo, rows_per_peer, col_offset, Lq, Lk, heads,
           head_dim, scale, _stream())

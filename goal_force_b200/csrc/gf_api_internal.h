@@ -17,6 +17,32 @@ int gf_num_sms();
 int gf_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
                          uint32_t box_inner, uint32_t box_outer);
 
+// Tensor map for (base, dims, pitch, box): looked up in / inserted into the context's cache when ctx != nullptr,
+// otherwise encoded into `scratch`.  Returns nullptr and sets *rc on failure.  A tensor map depends only on the
+// address and the geometry, never on the contents, so a cached entry stays valid when a buffer is freed and another
+// one with the same geometry lands on the same address.
+const CUtensorMap* gf_ctx_tmap(gf_ctx* ctx, CUtensorMap* scratch, const void* base, uint64_t inner, uint64_t outer,
+                               uint64_t ld, uint32_t box_inner, uint32_t box_outer, int* rc);
+
+// Per-context tuning (0 / negative = library default).
+struct CtxTuning {
+  int attn_impl = 0;       // 0: per shape (80 for long key sequences, 128 for Lk <= 1024); 80 / 128: forced
+  int attn_emu = -1;       // -1: kernel default; 0, 2, 4, 6: column pairs per 16 with exp2 on the FMA pipe
+  int gemm_group_m = 0;    // 0: per shape; > 0: rasterisation group height in m-tiles
+};
+CtxTuning gf_ctx_tuning(const gf_ctx* ctx);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): `done` is a per-kernel static array.
+inline int gf_set_smem_once(bool (&done)[64], const void* kern, int bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return GF_ERR_BAD_ARG;
+  if (done[dev]) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return (int)e;
+  done[dev] = true;
+  return 0;
+}
+
 // Where an attention kernel stores its output.  n_peers == 0: plain [Lq, ldo] buffer at base[0].  Otherwise the
 // Ulysses return path: global query row g goes to base[g / rows_per_peer] at row g % rows_per_peer (pitch ldo),
 // column col_offset + head*head_dim.
@@ -29,7 +55,7 @@ struct AttnOut {
 };
 
 // gf_attn80.cu: the decoupled 80-row-block attention kernel behind gf_attention_bf16 (arguments as the C ABI).
-int gf_attention80_launch(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+int gf_attention80_launch(gf_ctx* ctx, const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
                           const AttnOut& out, int Lq, int Lk, int heads, float scale, int emu_pairs,
                           cudaStream_t stream);
 

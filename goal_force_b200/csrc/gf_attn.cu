@@ -318,48 +318,25 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-// Kernel selection.  Defaults are what the benchmarks use; GF_ATTN_IMPL / GF_ATTN_EMU_PAIRS in the environment (read
-// once) or gf_attention_tuning() override them:
-//   impl      : 80 = gf_attn80.cu (decoupled, 80-row kv blocks, four softmax warpgroups; default),
-//               128 = this file (128-row kv blocks, P aliases S)
-//   emu_pairs : column pairs per 16 whose exponential runs on the FMA pipe instead of the MUFU (0, 2, 4, 6)
-static int g_attn_impl = -1, g_attn_emu = -1;
-static bool g_attn_forced = false;        // set by gf_attention_tuning / GF_ATTN_IMPL: no per-shape choice
-static int env_int(const char* name, int dflt) {
-  const char* e = std::getenv(name);
-  return e ? std::atoi(e) : dflt;
-}
-static int attn_impl() {
-  if (g_attn_impl < 0) {
-    g_attn_forced = std::getenv("GF_ATTN_IMPL") != nullptr;
-    g_attn_impl = env_int("GF_ATTN_IMPL", 80) == 128 ? 128 : 80;
-  }
-  return g_attn_impl;
-}
+// Kernel selection (per context, gf_ctx_set_attention; no process-wide state):
+//   impl      : 80 = gf_attn80.cu (decoupled, 80-row kv blocks, four softmax warpgroups),
+//               128 = this file (128-row kv blocks, P aliases S), 0 = per shape
+//   emu_pairs : column pairs per 16 whose exponential runs on the FMA pipe instead of the MUFU (0, 2, 4, 6);
+//               -1 = kernel default (0 for impl 80, 4 for impl 128)
 // Short key sequences (cross-attention against 512 context tokens) are a handful of kv blocks per CTA: there the
 // 128-row-block kernel wastes fewer padded columns (512 = 4 x 128 vs 7 x 80) and measures ~8 % faster.
-static int attn_impl_for(int Lk) {
-  const int impl = attn_impl();
-  return (!g_attn_forced && Lk <= 1024) ? 128 : impl;
+static int attn_impl_for(const CtxTuning& t, int Lk) {
+  if (t.attn_impl == 80 || t.attn_impl == 128) return t.attn_impl;
+  return Lk <= 1024 ? 128 : 80;
 }
-static int attn_emu_pairs() {
-  if (g_attn_emu < 0) {
-    const int v = env_int("GF_ATTN_EMU_PAIRS", attn_impl() == 80 ? 0 : 4);
-    g_attn_emu = (v == 0 || v == 2 || v == 4 || v == 6) ? v : 0;
-  }
-  return g_attn_emu;
-}
+static int attn_emu_for(const CtxTuning& t, int impl) { return t.attn_emu >= 0 ? t.attn_emu : (impl == 80 ? 0 : 4); }
 
 template <int kEmuPairs>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p,
                        cudaStream_t stream) {
   auto kern = gf_attn_kernel<kEmuPairs>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static bool configured[64] = {};
+  if (int rc = gf_set_smem_once(configured, reinterpret_cast<const void*>(kern), AT_SMEM_BYTES)) return rc;
   const dim3 grid(p.q_blocks * p.heads), block(AT_THREADS);
   kern<<<grid, block, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   return (int)cudaGetLastError();
@@ -367,16 +344,7 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
 
 }  // namespace gf
 
-extern "C" int gf_attention_tuning(int impl, int emu_pairs) {
-  if ((impl != 80 && impl != 128) || (emu_pairs != 0 && emu_pairs != 2 && emu_pairs != 4 && emu_pairs != 6))
-    return GF_ERR_BAD_ARG;
-  gf::g_attn_impl = impl;
-  gf::g_attn_emu = emu_pairs;
-  gf::g_attn_forced = true;
-  return 0;
-}
-
-static int attention_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+static int attention_dispatch(gf_ctx* ctx, const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
                               const gf::AttnOut& out, int Lq, int Lk, int heads, int head_dim, float scale,
                               void* stream) {
   using namespace gf;
@@ -386,38 +354,41 @@ static int attention_dispatch(const void* Q, long long ldq, const void* K, long 
   for (int i = 0; i < (out.n_peers ? out.n_peers : 1); ++i)
     if (!out.base[i] || (reinterpret_cast<uintptr_t>(out.base[i]) & 15)) return GF_ERR_BAD_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (attn_impl_for(Lk) == 80)
-    return gf_attention80_launch(Q, ldq, K, ldk, V, ldv, out, Lq, Lk, heads, scale, attn_emu_pairs(), s);
-  CUtensorMap tmQ, tmK, tmV;
-  int rc = gf_make_tmap_2d_bf16(&tmQ, Q, (uint64_t)heads * AT_D, (uint64_t)Lq, (uint64_t)ldq, 64, AT_BM);
-  if (rc) return rc;
-  rc = gf_make_tmap_2d_bf16(&tmK, K, (uint64_t)heads * AT_D, (uint64_t)Lk, (uint64_t)ldk, 64, AT_BN);
-  if (rc) return rc;
-  rc = gf_make_tmap_2d_bf16(&tmV, V, (uint64_t)heads * AT_D, (uint64_t)Lk, (uint64_t)ldv, 64, AT_BN);
-  if (rc) return rc;
+  const CtxTuning tune = gf_ctx_tuning(ctx);
+  const int impl = attn_impl_for(tune, Lk);
+  const int emu = attn_emu_for(tune, impl);
+  if (impl == 80) return gf_attention80_launch(ctx, Q, ldq, K, ldk, V, ldv, out, Lq, Lk, heads, scale, emu, s);
+  CUtensorMap scr[3];
+  int rc = 0;
+  const CUtensorMap* tmQ = gf_ctx_tmap(ctx, &scr[0], Q, (uint64_t)heads * AT_D, (uint64_t)Lq, (uint64_t)ldq, 64, AT_BM, &rc);
+  if (!tmQ) return rc;
+  const CUtensorMap* tmK = gf_ctx_tmap(ctx, &scr[1], K, (uint64_t)heads * AT_D, (uint64_t)Lk, (uint64_t)ldk, 64, AT_BN, &rc);
+  if (!tmK) return rc;
+  const CUtensorMap* tmV = gf_ctx_tmap(ctx, &scr[2], V, (uint64_t)heads * AT_D, (uint64_t)Lk, (uint64_t)ldv, 64, AT_BN, &rc);
+  if (!tmV) return rc;
   AttnParams p;
   p.out = out;
   p.Lq = Lq; p.Lk = Lk; p.heads = heads;
   p.q_blocks = (Lq + 2 * AT_BM - 1) / (2 * AT_BM);
   p.scale_log2 = scale * 1.4426950408889634f;
-  switch (g_attn_forced ? attn_emu_pairs() : 4) {
-    case 0: return launch_attn<0>(tmQ, tmK, tmV, p, s);
-    case 2: return launch_attn<2>(tmQ, tmK, tmV, p, s);
-    case 6: return launch_attn<6>(tmQ, tmK, tmV, p, s);
-    default: return launch_attn<4>(tmQ, tmK, tmV, p, s);
+  switch (emu) {
+    case 0: return launch_attn<0>(*tmQ, *tmK, *tmV, p, s);
+    case 2: return launch_attn<2>(*tmQ, *tmK, *tmV, p, s);
+    case 6: return launch_attn<6>(*tmQ, *tmK, *tmV, p, s);
+    default: return launch_attn<4>(*tmQ, *tmK, *tmV, p, s);
   }
 }
 
-extern "C" int gf_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V,
+extern "C" int gf_attention_bf16(gf_ctx* ctx, const void* Q, long long ldq, const void* K, long long ldk, const void* V,
                                  long long ldv, void* O, long long ldo, int Lq, int Lk, int heads, int head_dim,
                                  float scale, void* stream) {
   gf::AttnOut out{};
   out.base[0] = O;
   out.ldo = ldo;
-  return attention_dispatch(Q, ldq, K, ldk, V, ldv, out, Lq, Lk, heads, head_dim, scale, stream);
+  return attention_dispatch(ctx, Q, ldq, K, ldk, V, ldv, out, Lq, Lk, heads, head_dim, scale, stream);
 }
 
-extern "C" int gf_attention_scatter_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V,
+extern "C" int gf_attention_scatter_bf16(gf_ctx* ctx, const void* Q, long long ldq, const void* K, long long ldk, const void* V,
                                          long long ldv, void* const* O_peers, int n_peers, long long ldo,
                                          int rows_per_peer, int col_offset, int Lq, int Lk, int heads, int head_dim,
                                          float scale, void* stream) {
@@ -429,5 +400,5 @@ extern "C" int gf_attention_scatter_bf16(const void* Q, long long ldq, const voi
   out.n_peers = n_peers;
   out.rows_per_peer = rows_per_peer;
   out.col_offset = col_offset;
-  return attention_dispatch(Q, ldq, K, ldk, V, ldv, out, Lq, Lk, heads, head_dim, scale, stream);
+  return attention_dispatch(ctx, Q, ldq, K, ldk, V, ldv, out, Lq, Lk, heads, head_dim, scale, stream);
 }

@@ -356,27 +356,24 @@ template <int kEmuPairs>
 static int launch80(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const Attn80Params& p,
                     cudaStream_t stream) {
   auto kern = gf_attn80_kernel<kEmuPairs>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A8_SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static bool configured[64] = {};
+  if (int rc = gf_set_smem_once(configured, reinterpret_cast<const void*>(kern), A8_SMEM_BYTES)) return rc;
   const int items = p.q_blocks * p.heads;
   kern<<<dim3(p.n_full + 2 * (items - p.n_full)), dim3(A8_THREADS), A8_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   return (int)cudaGetLastError();
 }
 
-int gf_attention80_launch(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+int gf_attention80_launch(gf_ctx* ctx, const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
                           const AttnOut& out, int Lq, int Lk, int heads, float scale, int emu_pairs,
                           cudaStream_t stream) {
-  CUtensorMap tmQ, tmK, tmV;
-  int rc = gf_make_tmap_2d_bf16(&tmQ, Q, (uint64_t)heads * A8_D, (uint64_t)Lq, (uint64_t)ldq, 64, A8_BM);
-  if (rc) return rc;
-  rc = gf_make_tmap_2d_bf16(&tmK, K, (uint64_t)heads * A8_D, (uint64_t)Lk, (uint64_t)ldk, 64, A8_BN);
-  if (rc) return rc;
-  rc = gf_make_tmap_2d_bf16(&tmV, V, (uint64_t)heads * A8_D, (uint64_t)Lk, (uint64_t)ldv, 64, A8_BN);
-  if (rc) return rc;
+  CUtensorMap scr[3];
+  int rc = 0;
+  const CUtensorMap* tmQ = gf_ctx_tmap(ctx, &scr[0], Q, (uint64_t)heads * A8_D, (uint64_t)Lq, (uint64_t)ldq, 64, A8_BM, &rc);
+  if (!tmQ) return rc;
+  const CUtensorMap* tmK = gf_ctx_tmap(ctx, &scr[1], K, (uint64_t)heads * A8_D, (uint64_t)Lk, (uint64_t)ldk, 64, A8_BN, &rc);
+  if (!tmK) return rc;
+  const CUtensorMap* tmV = gf_ctx_tmap(ctx, &scr[2], V, (uint64_t)heads * A8_D, (uint64_t)Lk, (uint64_t)ldv, 64, A8_BN, &rc);
+  if (!tmV) return rc;
   Attn80Params p;
   p.out = out;
   p.Lq = Lq; p.Lk = Lk; p.heads = heads;
@@ -387,10 +384,10 @@ int gf_attention80_launch(const void* Q, long long ldq, const void* K, long long
   p.n_full = (tail > 0 && items > sms && 2 * tail <= sms) ? items - tail : items;
   p.scale_log2 = scale * 1.4426950408889634f;
   switch (emu_pairs) {
-    case 0: return launch80<0>(tmQ, tmK, tmV, p, stream);
-    case 2: return launch80<2>(tmQ, tmK, tmV, p, stream);
-    case 6: return launch80<6>(tmQ, tmK, tmV, p, stream);
-    default: return launch80<4>(tmQ, tmK, tmV, p, stream);
+    case 0: return launch80<0>(*tmQ, *tmK, *tmV, p, stream);
+    case 2: return launch80<2>(*tmQ, *tmK, *tmV, p, stream);
+    case 6: return launch80<6>(*tmQ, *tmK, *tmV, p, stream);
+    default: return launch80<4>(*tmQ, *tmK, *tmV, p, stream);
   }
 }
 

@@ -19,7 +19,6 @@
 //   warps 2..5  : epilogue: tcgen05.ld accumulator -> registers -> fused math -> 16-byte global stores
 //   TMEM        : 2 accumulator stages x 256 fp32 columns (all 512 columns), so the epilogue of tile i overlaps the
 //                 MMAs of tile i+1.
-#include <cstdlib>
 #include "gf_ptx.cuh"
 #include "gf_api_internal.h"
 
@@ -261,12 +260,8 @@ template <int kCG, int EPI>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<kCG>;
   auto kern = gf_gemm_kernel<kCG, EPI>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static bool configured[64] = {};
+  if (int rc = gf_set_smem_once(configured, reinterpret_cast<const void*>(kern), Cfg::kSmemBytes)) return rc;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   int clusters = gf_num_sms() / kCG;
   if (clusters > tiles) clusters = tiles;
@@ -298,7 +293,7 @@ static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, con
 
 }  // namespace gf
 
-extern "C" int gf_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
+extern "C" int gf_gemm_bf16(gf_ctx* ctx, const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
                             int N, int K, const void* bias, int epi, const void* gate, const void* R, long long ldr,
                             int cta_group, void* stream) {
   using namespace gf;
@@ -308,11 +303,13 @@ extern "C" int gf_gemm_bf16(const void* A, long long lda, const void* W, long lo
   if (cta_group != 1 && cta_group != 2) return GF_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) & 15)
     return GF_ERR_BAD_ARG;
-  CUtensorMap tmA, tmB;
-  int rc = gf_make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM);
-  if (rc) return rc;
-  rc = gf_make_tmap_2d_bf16(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GEMM_BK, GEMM_BN / cta_group);
-  if (rc) return rc;
+  CUtensorMap scrA, scrB;
+  int rc = 0;
+  const CUtensorMap* tmA = gf_ctx_tmap(ctx, &scrA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM, &rc);
+  if (!tmA) return rc;
+  const CUtensorMap* tmB =
+      gf_ctx_tmap(ctx, &scrB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GEMM_BK, GEMM_BN / cta_group, &rc);
+  if (!tmB) return rc;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.C = reinterpret_cast<__nv_bfloat16*>(C); p.ldc = ldc;
@@ -321,17 +318,11 @@ extern "C" int gf_gemm_bf16(const void* A, long long lda, const void* W, long lo
   p.R = reinterpret_cast<const __nv_bfloat16*>(R); p.ldr = ldr;
   p.num_m_tiles = (M + GEMM_BM * cta_group - 1) / (GEMM_BM * cta_group);
   p.num_n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
-  {
-    // Rasterisation: tiles walk `group_m` m-tiles before moving along N.  Measured under sustained load at M = 32760
-    // (tools/gpu_check.py gemm_sustained): 16 is best for K = 5120 (each operand slab of a tile is 2.6 MB), 8 for
-    // K = 13824 (7 MB slabs: a taller group no longer fits L2 next to the W columns in flight); 4 and 32 lose 6-10 %.
-    static int forced = -1;
-    if (forced < 0) {
-      const char* e = std::getenv("GF_GEMM_GROUP_M");
-      forced = e ? std::atoi(e) : 0;
-    }
-    p.group_m = forced > 0 ? forced : (K <= 8192 ? 2 * GEMM_GROUP_M : GEMM_GROUP_M);
-  }
+  // Rasterisation: tiles walk `group_m` m-tiles before moving along N.  Measured under sustained load at M = 32760
+  // (tools/gpu_check.py gemm_sustained): 16 is best for K = 5120 (each operand slab of a tile is 2.6 MB), 8 for
+  // K = 13824 (7 MB slabs: a taller group no longer fits L2 next to the W columns in flight); 4 and 32 lose 6-10 %.
+  const int forced = gf_ctx_tuning(ctx).gemm_group_m;
+  p.group_m = forced > 0 ? forced : (K <= 8192 ? 2 * GEMM_GROUP_M : GEMM_GROUP_M);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  return cta_group == 1 ? dispatch_epi<1>(epi, tmA, tmB, p, s) : dispatch_epi<2>(epi, tmA, tmB, p, s);
+  return cta_group == 1 ? dispatch_epi<1>(epi, *tmA, *tmB, p, s) : dispatch_epi<2>(epi, *tmA, *tmB, p, s);
 }

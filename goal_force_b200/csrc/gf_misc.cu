@@ -55,6 +55,25 @@ __global__ void add_rows_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
     y[i] = __float2bfloat16_rn(__bfloat162float(a[i]) + __bfloat162float(b[i % cols]));
 }
 
+// y = a + b elementwise (one bf16 rounding, as torch's bf16 add); y may alias a or b, so no __restrict__.
+// n8 = number of 8-element (16-byte) vectors; the scalar tail is handled by the last threads.
+__global__ void add_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, long long n) {
+  const long long n8 = n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const uint4 va = reinterpret_cast<const uint4*>(a)[i];
+    const uint4 vb = reinterpret_cast<const uint4*>(b)[i];
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[k] = pack_bf16x2(bf16_lo(wa[k]) + bf16_lo(wb[k]), bf16_hi(wa[k]) + bf16_hi(wb[k]));
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  for (long long i = (n8 << 3) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = __float2bfloat16_rn(__bfloat162float(a[i]) + __bfloat162float(b[i]));
+}
+
 __global__ void silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = __bfloat162float(x[i]);
@@ -64,7 +83,7 @@ __global__ void silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* 
 
 // pred = nega + s*(posi - nega) ; out = lat + pred*dsigma, bf16 rounding after each torch op of the reference
 __global__ void cfg_euler_kernel(const __nv_bfloat16* __restrict__ posi, const __nv_bfloat16* __restrict__ nega,
-                                 const __nv_bfloat16* __restrict__ lat, __nv_bfloat16* __restrict__ out, float s,
+                                 const __nv_bfloat16* lat, __nv_bfloat16* out /* may alias lat */, float s,
                                  float dsigma, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float p = __bfloat162float(posi[i]);
@@ -163,6 +182,14 @@ extern "C" int gf_add_rows_bf16(const void* a, const void* b, void* y, int rows,
   if (!a || !b || !y || rows <= 0 || cols <= 0) return GF_ERR_BAD_ARG;
   add_rows_kernel<<<grid_for((long long)rows * cols, 256), 256, 0, GF_STREAM(stream)>>>((const bf16*)a, (const bf16*)b,
                                                                                        (bf16*)y, rows, cols);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gf_add_bf16(const void* a, const void* b, void* y, long long n, void* stream) {
+  if (!a || !b || !y || n <= 0) return GF_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15)
+    return GF_ERR_BAD_ARG;
+  add_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, GF_STREAM(stream)>>>((const bf16*)a, (const bf16*)b, (bf16*)y, n);
   return (int)cudaGetLastError();
 }
 

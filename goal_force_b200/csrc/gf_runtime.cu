@@ -2,7 +2,36 @@
 // libcuda is resolved at run time through cudaGetDriverEntryPoint so the library loads (and exports its symbols)
 // on a machine without a driver; compute entry points then fail with GF_ERR_NO_DRIVER instead of crashing.
 #include <mutex>
+#include <new>
+#include <unordered_map>
 #include "gf_api_internal.h"
+
+// The opaque context of the C ABI: cached TMA descriptors and per-context tuning.  No process-wide state: two
+// contexts (e.g. two pipelines in one process) never see each other's settings.
+struct gf_ctx {
+  struct Key {
+    const void* base;
+    uint64_t inner, outer, ld;
+    uint32_t box_inner, box_outer;
+    bool operator==(const Key& o) const {
+      return base == o.base && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
+             box_outer == o.box_outer;
+    }
+  };
+  struct Hash {
+    size_t operator()(const Key& k) const {
+      uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+      h ^= (k.inner + 0x632BE59BD9B4E019ull) + (h << 6) + (h >> 2);
+      h ^= (k.outer * 0xD6E8FEB86659FD93ull) + (h << 6) + (h >> 2);
+      h ^= (k.ld * 31 + k.box_inner * 7 + k.box_outer) + (h << 6) + (h >> 2);
+      return (size_t)h;
+    }
+  };
+  std::mutex mu;
+  std::unordered_map<Key, CUtensorMap, Hash> tmaps;
+  long long hits = 0, misses = 0;
+  gf::CtxTuning tuning;
+};
 
 namespace gf {
 
@@ -51,7 +80,67 @@ int gf_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uin
   return r == CUDA_SUCCESS ? 0 : GF_ERR_TMAP;
 }
 
+const CUtensorMap* gf_ctx_tmap(gf_ctx* ctx, CUtensorMap* scratch, const void* base, uint64_t inner, uint64_t outer,
+                               uint64_t ld, uint32_t box_inner, uint32_t box_outer, int* rc) {
+  *rc = 0;
+  if (!ctx) {
+    *rc = gf_make_tmap_2d_bf16(scratch, base, inner, outer, ld, box_inner, box_outer);
+    return *rc ? nullptr : scratch;
+  }
+  const gf_ctx::Key key{base, inner, outer, ld, box_inner, box_outer};
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  auto it = ctx->tmaps.find(key);
+  if (it != ctx->tmaps.end()) {
+    ++ctx->hits;
+    return &it->second;          // unordered_map never moves its nodes: the pointer stays valid until clear()
+  }
+  ++ctx->misses;
+  *rc = gf_make_tmap_2d_bf16(scratch, base, inner, outer, ld, box_inner, box_outer);
+  if (*rc) return nullptr;
+  if (ctx->tmaps.size() >= 16384) return scratch;   // bounded: beyond this, behave like the stateless path
+  return &ctx->tmaps.emplace(key, *scratch).first->second;
+}
+
+CtxTuning gf_ctx_tuning(const gf_ctx* ctx) { return ctx ? ctx->tuning : CtxTuning{}; }
+
 }  // namespace gf
+
+extern "C" int gf_ctx_create(gf_ctx** ctx) {
+  if (!ctx) return GF_ERR_BAD_ARG;
+  *ctx = new (std::nothrow) gf_ctx();
+  return *ctx ? 0 : GF_ERR_BAD_ARG;
+}
+
+extern "C" int gf_ctx_destroy(gf_ctx* ctx) {
+  if (!ctx) return GF_ERR_BAD_ARG;
+  delete ctx;
+  return 0;
+}
+
+extern "C" int gf_ctx_set_attention(gf_ctx* ctx, int impl, int emu_pairs) {
+  if (!ctx) return GF_ERR_BAD_ARG;
+  if ((impl != 0 && impl != 80 && impl != 128) ||
+      (emu_pairs != -1 && emu_pairs != 0 && emu_pairs != 2 && emu_pairs != 4 && emu_pairs != 6))
+    return GF_ERR_BAD_ARG;
+  ctx->tuning.attn_impl = impl;
+  ctx->tuning.attn_emu = emu_pairs;
+  return 0;
+}
+
+extern "C" int gf_ctx_set_gemm_raster(gf_ctx* ctx, int group_m) {
+  if (!ctx || group_m < 0 || group_m > 1024) return GF_ERR_BAD_ARG;
+  ctx->tuning.gemm_group_m = group_m;
+  return 0;
+}
+
+extern "C" int gf_ctx_stats(gf_ctx* ctx, long long* tmap_entries, long long* tmap_hits, long long* tmap_misses) {
+  if (!ctx) return GF_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (tmap_entries) *tmap_entries = (long long)ctx->tmaps.size();
+  if (tmap_hits) *tmap_hits = ctx->hits;
+  if (tmap_misses) *tmap_misses = ctx->misses;
+  return 0;
+}
 
 extern "C" int gf_abi_version(void) { return GF_ABI_VERSION; }
 extern "C" int gf_device_sms(void) { return gf::gf_num_sms(); }

@@ -12,6 +12,7 @@ goal_force_b200.capi; torch only owns memory and streams. There is no CPU / eage
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -115,6 +116,14 @@ class _Workspace:
         self.ao = torch.empty((L, d), **bf)
         self.qc = torch.empty((L, d), **bf)
         self.u = torch.empty((L, cfg.ffn_dim), **bf)
+        self._cn_states = None
+
+    def cn_states(self, n: int) -> torch.Tensor:
+        """[n, L, dim] outputs of the ControlNet blocks (a17); block i reads state i-1 and writes state i, so the
+        branch needs no copies.  Allocated on first use (3.4 GB for 10 layers at 32,760 tokens)."""
+        if self._cn_states is None or self._cn_states.shape[0] < n:
+            self._cn_states = torch.empty((n, self.L, self.h.shape[1]), dtype=torch.bfloat16, device=self.h.device)
+        return self._cn_states[:n]
 
 
 _WORKSPACES: dict = {}
@@ -142,10 +151,13 @@ class PeerExchange:
     def __init__(self, dist, group, rank: int, size: int, Ll: int, d: int, device):
         if size > 8:
             raise ValueError("peer exchange is limited to the 8 GPUs of one NVSwitch domain")
+        self.dist, self.group = dist, group
         self.rank, self.size, self.Ll, self.d = rank, size, Ll, d
         self.w = d // size
+        self.timeout_ms = int(os.environ.get("GF_PEER_TIMEOUT_MS", "60000"))   # read once, not on the launch path
         sizes = {"recv": size * Ll * 3 * self.w * 2, "ao": Ll * d * 2, "flags": 256}
         self.local = {k: capi.peer_alloc(n) for k, n in sizes.items()}
+        self.status = capi.PeerStatus()
         mine = {k: capi.peer_export(p) for k, p in self.local.items()}
         everyone = [None] * size
         dist.all_gather_object(everyone, mine, group=group)
@@ -162,22 +174,46 @@ class PeerExchange:
         self.recv_ptrs, self.ao_ptrs, self.flag_ptrs = (capi.ptr_array(ptrs[k]) for k in ("recv", "ao", "flags"))
         self.recv = capi.as_bf16_tensor(self.local["recv"], (size * Ll, 3 * self.w), device)
         self.ao = capi.as_bf16_tensor(self.local["ao"], (Ll, d), device)
-        self.epoch = 0
         dist.barrier(group=group)          # every rank has mapped every buffer before anybody writes
+        _LIVE_EXCHANGES.append(self)
 
     def barrier(self) -> None:
         """All ranks' earlier kernels (on their compute streams) are complete and visible when this returns on the
-        stream; the only collective left in the exchange."""
-        self.epoch += 1
-        capi.peer_barrier(self.flag_ptrs, self.size, self.rank, self.epoch)
+        stream; the only collective left in the exchange.  The epoch counter lives in the flag buffer."""
+        capi.peer_barrier(self.flag_ptrs, self.size, self.rank, self.timeout_ms, self.status)
+
+    def check(self) -> None:
+        """Raise if a barrier of an earlier forward timed out (reads a host-mapped word; no stream sync)."""
+        self.status.check()
 
     def close(self) -> None:
+        """Collective teardown: drain my stream, unmap the peers' buffers, wait until every rank has unmapped mine
+        (cudaFree of memory a peer still has IPC-mapped is undefined), then free."""
+        if not self.local:
+            return
+        torch.cuda.synchronize()
         for p in self._imported:
             capi.peer_unimport(p)
         self._imported = []
+        try:
+            self.dist.barrier(group=self.group)
+        except Exception:  # noqa: BLE001 - process group already destroyed at interpreter exit
+            pass
         for p in self.local.values():
             capi.peer_free(p)
         self.local = {}
+        self.status.free()
+        if self in _LIVE_EXCHANGES:
+            _LIVE_EXCHANGES.remove(self)
+
+
+_LIVE_EXCHANGES: list = []      # creation order (identical on every rank, so teardown barriers pair up)
+
+
+def close_peer_exchanges() -> None:
+    """Tear down every live PeerExchange (collective: call on all ranks, before destroy_process_group)."""
+    for ex in list(_LIVE_EXCHANGES):
+        ex.close()
 
 
 class SequenceParallel:
@@ -229,6 +265,15 @@ class SequenceParallel:
             self._peer = {key: ex}
         return ex
 
+    def check(self) -> None:
+        for ex in self._peer.values():
+            ex.check()
+
+    def close(self) -> None:
+        for ex in self._peer.values():
+            ex.close()
+        self._peer = {}
+
     def _check_heads(self, heads: int) -> int:
         if heads % self.size:
             raise ValueError(f"{heads} heads do not divide over {self.size} ranks")
@@ -268,15 +313,18 @@ class SequenceParallel:
 
 
 def run_block(bw: _Block, cfg: DiTConfig, x: torch.Tensor, ctx_kv: torch.Tensor, mod: torch.Tensor,
-              cos_sin: torch.Tensor, ws: _Workspace, sp: SequenceParallel | None = None) -> None:
-    """DiTBlock.forward (wan_video_dit.py:214-230) in place on x [L, dim].
+              cos_sin: torch.Tensor, ws: _Workspace, sp: SequenceParallel | None = None,
+              x_in: torch.Tensor | None = None) -> None:
+    """DiTBlock.forward (wan_video_dit.py:214-230) on [L, dim] tokens: in place on x, or from x_in into x (x_in is
+    left untouched: the first residual GEMM reads it and writes x).
     mod: [6, dim] = modulation + t_mod (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp);
     ctx_kv: [ctx_len, 2*dim] cached cross-attention keys (RMS-normed) | values of this block."""
     d, H, eps = cfg.dim, cfg.num_heads, cfg.eps
     L = x.shape[0]
     h, qkv, ao, qc, u = ws.h[:L], ws.qkv[:L], ws.ao[:L], ws.qc[:L], ws.u[:L]
+    src = x if x_in is None else x_in
     # --- self attention
-    capi.layernorm(x, eps=eps, shift=mod[0], scale=mod[1], out=h)
+    capi.layernorm(src, eps=eps, shift=mod[0], scale=mod[1], out=h)
     capi.gemm(h, bw.wqkv, bw.bqkv, out=qkv)
     if sp is not None and sp.size > 1 and sp.transport == "peer":
         attn = sp.self_attention_fused(qkv, bw.norm_q, bw.norm_k, eps, cos_sin, H)
@@ -287,7 +335,7 @@ def run_block(bw: _Block, cfg: DiTConfig, x: torch.Tensor, ctx_kv: torch.Tensor,
         else:
             sp.self_attention(qkv, H, ao)
         attn = ao
-    capi.gemm(attn, bw.wo, bw.bo, epi=capi.GF_EPI_GATE_RES, gate=mod[2], residual=x, out=x)
+    capi.gemm(attn, bw.wo, bw.bo, epi=capi.GF_EPI_GATE_RES, gate=mod[2], residual=src, out=x)
     # --- cross attention
     capi.layernorm(x, eps=eps, weight=bw.n3w, bias=bw.n3b, out=h)
     capi.gemm(h, bw.cq_w, bw.cq_b, out=qc)
@@ -352,12 +400,20 @@ class WanModelB200:
         """Build from a reference diffsynth WanModel instance (weights are copied to bf16 kernel layout)."""
         if getattr(module, "has_image_input", False):
             raise NotImplementedError("has_image_input=True (CLIP image branch) is outside the goal-force hot path")
+        for flag in ("seperated_timestep", "fuse_vae_embedding_in_latents", "has_ref_conv", "has_image_pos_emb"):
+            if getattr(module, flag, False):
+                raise NotImplementedError(f"WanModel variant with {flag}=True is outside the goal-force hot path")
+        if getattr(module, "control_adapter", None) is not None:
+            raise NotImplementedError("WanModel with a control adapter is outside the goal-force hot path")
         blk = module.blocks[0]
         cfg = DiTConfig(dim=module.dim, in_dim=module.in_dim, ffn_dim=blk.ffn_dim, out_dim=module.head.head.out_features // 4,
                         text_dim=module.text_embedding[0].in_features, freq_dim=module.freq_dim,
                         eps=blk.norm1.eps, num_heads=blk.num_heads, num_layers=len(module.blocks),
                         patch_size=tuple(module.patch_size))
-        return cls(cfg, module.state_dict(), device=device)
+        out = cls(cfg, module.state_dict(), device=device)
+        out.require_vae_embedding = bool(getattr(module, "require_vae_embedding", True))
+        out.require_clip_embedding = bool(getattr(module, "require_clip_embedding", False))
+        return out
 
     # -------------------------------------------------------------------------------------------- step-invariant
     def rope(self, f: int, h: int, w: int, sp: SequenceParallel | None = None) -> torch.Tensor:
@@ -369,26 +425,33 @@ class WanModelB200:
             self._rope_cache = {key: t}
         return t
 
-    def context_kv(self, context: torch.Tensor) -> list:
+    def context_entry(self, context: torch.Tensor) -> tuple:
         """text_embedding (wan_video_dit.py:309-313,371) + per-block cross-attention K/V, cached per context tensor
-        (the pipeline passes the same prompt embedding at every step)."""
-        key = (context.data_ptr(), context._version, tuple(context.shape))
-        hit = self._ctx_cache.get(key)      # the cached entry keeps `context` alive, so the key cannot be recycled
+        (the pipeline passes the same prompt embedding at every step).  Returns the cache entry
+        (context, [K|V per block], embedding); the entry keeps `context` alive, so its address cannot be recycled
+        while the entry is cached.  Tensors without a version counter (torch.inference_mode) are not cached."""
+        try:
+            key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype)
+        except RuntimeError:
+            key = None
+        hit = self._ctx_cache.get(key) if key is not None else None
         if hit is not None:
-            return hit[1]
+            return hit
         ctx = context.reshape(-1, context.shape[-1]).to(device=self.device, dtype=torch.bfloat16).contiguous()
         e = capi.gemm(ctx, self.text0_w, self.text0_b, epi=capi.GF_EPI_BIAS_GELU)
         e = capi.gemm(e, self.text2_w, self.text2_b)
-        kvs = [block_context_kv(b, self.cfg, e) for b in self.blocks]
-        if len(self._ctx_cache) >= 4:
-            self._ctx_cache.clear()
-        self._ctx_cache[key] = (context, kvs, e)
-        return kvs
+        entry = (context, [block_context_kv(b, self.cfg, e) for b in self.blocks], e)
+        if key is not None:
+            if len(self._ctx_cache) >= 4:
+                self._ctx_cache.clear()
+            self._ctx_cache[key] = entry
+        return entry
+
+    def context_kv(self, context: torch.Tensor) -> list:
+        return self.context_entry(context)[1]
 
     def context_embedding(self, context: torch.Tensor) -> torch.Tensor:
-        self.context_kv(context)
-        key = (context.data_ptr(), context._version, tuple(context.shape))
-        return self._ctx_cache[key][2]
+        return self.context_entry(context)[2]
 
     def time_modulation(self, timestep: torch.Tensor):
         """t = time_embedding(sinusoidal(timestep)); t_mod = time_projection(t) (wan_video_dit.py:368-370);
@@ -509,17 +572,22 @@ class ControlNetB200:
         self._patch_cache = {key: (control_latents, tok)}
         return tok
 
-    def context_kv(self, ctx_key, ctx_emb: torch.Tensor) -> list:
-        hit = self._ctx_cache.get(ctx_key)
-        if hit is None:
-            hit = [block_context_kv(b, self.cfg, ctx_emb) for b in self.blocks]
-            if len(self._ctx_cache) >= 4:
-                self._ctx_cache.clear()
-            self._ctx_cache[ctx_key] = hit
-        return hit
+    def context_kv(self, entry: tuple) -> list:
+        """Cross-attention K|V of the ControlNet blocks for one prompt.  `entry` is the trunk's cache entry
+        (WanModelB200.context_entry): the ControlNet result is keyed by that object's identity and keeps it -- and
+        with it the context tensor -- alive, so a recycled address or a trunk-side eviction can never alias a stale
+        ControlNet entry."""
+        hit = self._ctx_cache.get(id(entry))
+        if hit is not None and hit[0] is entry:
+            return hit[1]
+        kvs = [block_context_kv(b, self.cfg, entry[2]) for b in self.blocks]
+        if len(self._ctx_cache) >= 4:
+            self._ctx_cache.clear()
+        self._ctx_cache[id(entry)] = (entry, kvs)
+        return kvs
 
 
-_CONVERTED: dict = {}
+_CONVERTED: dict = {}      # id(reference module) -> (weakref, fingerprint, converted)
 _DEFAULT_SP: list = []
 
 
@@ -534,17 +602,48 @@ def _default_sequence_parallel() -> "SequenceParallel | None":
     return _DEFAULT_SP[0]
 
 
+def _fingerprint(module) -> tuple:
+    """Cheap identity of a reference module's weights: storage address and in-place version counter of every
+    parameter / buffer.  load_state_dict, LoRA merges, .to(device) and optimiser steps all change it."""
+    return tuple((t.data_ptr(), t._version, t.device.index) for t in module.state_dict(keep_vars=True).values())
+
+
+def _module_device(module):
+    """Device the converted copy lives on: the module's own CUDA device, else the current CUDA device."""
+    for t in module.parameters():
+        if t.is_cuda:
+            return t.device
+        break
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def convert(obj, kind=None, device=None):
+    """Explicit conversion / refresh of a reference nn.Module (WanModel or the goal-force ControlNet) into kernel
+    layout.  model_fn_wan_video calls this lazily; call it yourself after changing weights in a way the fingerprint
+    cannot see, or to convert ahead of the first step.  The cache holds the reference module only weakly."""
+    import weakref
+    if kind is None:
+        kind = ControlNetB200 if hasattr(obj, "controlnet_dit") else WanModelB200
+    key = id(obj)
+    conv = kind.from_reference(obj, device=device or _module_device(obj))
+
+    def _drop(_ref, key=key):
+        _CONVERTED.pop(key, None)
+
+    _CONVERTED[key] = (weakref.ref(obj, _drop), _fingerprint(obj), conv)
+    return conv
+
+
 def _as_b200(obj, kind):
-    """Accept our classes, or reference nn.Modules (converted once and cached by identity)."""
+    """Accept our classes, or reference nn.Modules.  A module is converted on first use and re-converted whenever
+    its weights change (pipe.load_lora, load_controlnet_weights after a warm-up call, .to(device)): the cache entry is
+    keyed by identity, validated by a weight fingerprint, and `ControlNetB200.is_noop` is recomputed with it."""
     if obj is None or isinstance(obj, kind):
         return obj
     hit = _CONVERTED.get(id(obj))
-    if hit is not None and hit[0] is obj:
-        return hit[1]
-    dev = "cuda"
-    conv = kind.from_reference(obj, device=dev)
-    _CONVERTED[id(obj)] = (obj, conv)
-    return conv
+    if hit is not None and hit[0]() is obj and hit[1] == _fingerprint(obj):
+        return hit[2]
+    return convert(obj, kind)
 
 
 def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None, timestep=None, context=None,
@@ -581,6 +680,8 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
     if sequence_parallel is None and use_unified_sequence_parallel:
         sequence_parallel = _default_sequence_parallel()
     sp = sequence_parallel if (sequence_parallel is not None and sequence_parallel.size > 1) else None
+    if sp is not None:
+        sp.check()                      # a barrier of an earlier forward timed out -> raise instead of going on
 
     B = max(latents.shape[0], context.shape[0])            # merged-CFG batches replicate latents (:1451-1454)
     outs = []
@@ -591,7 +692,8 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
         if y is not None and dit.require_vae_embedding:
             yb = y[min(b, y.shape[0] - 1)].to(device=dit.device, dtype=torch.bfloat16).contiguous()
         ctx_b = context[b:b + 1] if context.shape[0] > 1 else context
-        ctx_kv = dit.context_kv(ctx_b)
+        ctx_entry = dit.context_entry(ctx_b)
+        ctx_kv = ctx_entry[1]
         x, (f, h, w) = dit.patchify(lat, yb)                                                    # :1464
         L = f * h * w
         if sp is not None:
@@ -608,22 +710,22 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
             s = controlnet.control_tokens(csl)
             if s.shape[0] != L:
                 raise ValueError("control latents and latents have different token counts")
-            s = (s[sp.token_slice(L)] if sp is not None else s).clone()
-            ckey = (ctx_b.data_ptr(), ctx_b._version, id(dit))
-            cn_kv = controlnet.context_kv(ckey, dit.context_embedding(ctx_b))
+            if sp is not None:
+                s = s[sp.token_slice(L)]
+            cn_kv = controlnet.context_kv(ctx_entry)
             # ControlNet blocks share t_mod with the trunk but carry their own modulation tables
             cn_tab = capi.add_rows(controlnet.block_mod, t_mod_flat).view(controlnet.num_layers, 6, cfg.dim)
-            states = []
+            states = ws.cn_states(controlnet.num_layers)       # block i: state i-1 (or the patch tokens) -> state i
             for i, bw in enumerate(controlnet.blocks):
-                run_block(bw, cfg, s, cn_kv[i], cn_tab[i], cos_sin, ws, sp)
-                states.append(s.clone() if i + 1 < controlnet.num_layers else s)
+                run_block(bw, cfg, states[i], cn_kv[i], cn_tab[i], cos_sin, ws, sp, x_in=s)
+                s = states[i]
 
         for i, bw in enumerate(dit.blocks):                                                     # :1540-1570
             run_block(bw, cfg, x, ctx_kv[i], block_tab[i], cos_sin, ws, sp)
             if use_cn:
                 if controlnet.stride is not None:
                     if i % controlnet.stride == 0 and i // controlnet.stride < len(states):
-                        capi.add_rows(x.view(1, -1), states[i // controlnet.stride].view(-1), out=x.view(1, -1))
+                        capi.add_(x, states[i // controlnet.stride])
                 elif i < controlnet.num_layers:
                     capi.gemm(states[i], controlnet.zero_w[i], controlnet.zero_b[i], epi=capi.GF_EPI_GATE_RES,
                               gate=None, residual=x, out=x)

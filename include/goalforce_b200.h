@@ -8,6 +8,11 @@
  *   - all tensors are device pointers to row-major bf16 unless stated; the caller owns every buffer (kernels never
  *     allocate); pointers must be 16-byte aligned and row pitches ("ld*", in elements) multiples of 8;
  *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous and re-entrant per stream;
+ *   - the library keeps no process-wide state: tuning and cached TMA descriptors live in an opaque `gf_ctx` that the
+ *     tensor-core entry points take as their first argument (NULL = stateless call with default tuning); a context
+ *     may be used by one thread at a time per call, its descriptor cache is internally locked;
+ *   - the only allocations the library makes are the explicit gf_peer_alloc / gf_peer_status_alloc / gf_ctx_create
+ *     objects; compute entry points never allocate;
  *   - return value: 0 on success, a GF_ERR_* code (< 0) for rejected arguments, or a positive cudaError_t.
  */
 #ifndef GOALFORCE_B200_H_
@@ -17,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GF_ABI_VERSION 1
+#define GF_ABI_VERSION 2
 
 #define GF_ERR_BAD_ARG (-1)      /* null pointer, misaligned pointer/pitch, unsupported size */
 #define GF_ERR_NO_DRIVER (-2)    /* cuTensorMapEncodeTiled not resolvable (no driver / no GPU) */
@@ -35,6 +40,18 @@ extern "C" {
 
 int gf_abi_version(void);
 
+/* Opaque per-caller context: TMA descriptor cache (keyed by address + geometry, so a descriptor is encoded once per
+ * buffer instead of once per launch) and tuning.  gf_ctx_set_attention: impl 0 = per-shape choice (80-row decoupled
+ * kernel for long key sequences, 128-row kernel for Lk <= 1024), 80 / 128 = forced; emu_pairs -1 = kernel default, or
+ * 0/2/4/6 column pairs per 16 whose exp2 runs on the FMA pipe.  gf_ctx_set_gemm_raster: rasterisation group height in
+ * m-tiles, 0 = per-shape choice.  gf_ctx_stats: descriptor-cache counters (any pointer may be NULL). */
+typedef struct gf_ctx gf_ctx;
+int gf_ctx_create(gf_ctx** ctx);
+int gf_ctx_destroy(gf_ctx* ctx);
+int gf_ctx_set_attention(gf_ctx* ctx, int impl, int emu_pairs);
+int gf_ctx_set_gemm_raster(gf_ctx* ctx, int group_m);
+int gf_ctx_stats(gf_ctx* ctx, long long* tmap_entries, long long* tmap_hits, long long* tmap_misses);
+
 /* Number of SMs of the current CUDA device (148 on B200); <= 0 if no device. */
 int gf_device_sms(void);
 
@@ -43,7 +60,7 @@ int gf_device_sms(void);
  * k=1 Conv1d zero-conv at src/goal_force/wan_video_new.py:1564-1570.
  * bias/gate: [N] bf16 or NULL.  R: [M,ldr] residual for GF_EPI_GATE_RES (may alias C).  N % 32 == 0, K % 8 == 0.
  * cta_group: 1 = one CTA per 128x256 tile, 2 = CTA pair (cta_group::2) per 256x256 tile. */
-int gf_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
+int gf_gemm_bf16(gf_ctx* ctx, const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
                  int K, const void* bias, int epi, const void* gate, const void* R, long long ldr, int cta_group,
                  void* stream);
 
@@ -72,16 +89,8 @@ int gf_qk_rmsnorm_rope_bf16(void* qkv, long long ld, int rows, int d, const void
  * Replaces flash_attention() (wan_video_dit.py:28-61) for self-attention (Lk == Lq ~ 32k) and cross-attention
  * (Lk = 512).  Element (row, head, j) of Q lives at Q[row*ldq + head*head_dim + j]; same for K, V, O.
  * head_dim must be 128. */
-int gf_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+int gf_attention_bf16(gf_ctx* ctx, const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
                       void* O, long long ldo, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
-
-/* Forces the attention kernel behind gf_attention_bf16 (process-wide; results agree to rounding).  Without this call
- * (and without GF_ATTN_IMPL in the environment) the library picks per shape: impl 80 for long key sequences, impl 128
- * for Lk <= 1024 (cross-attention).
- *   impl 80  : decoupled kernel, 80-row kv blocks, S and P in separate TMEM columns, four softmax warpgroups (default)
- *   impl 128 : 128-row kv blocks, P aliases S in TMEM, two softmax warpgroups
- *   emu_pairs in {0, 2, 4, 6}: column pairs per 16 whose exp2 runs on the FMA pipe (polynomial) instead of the MUFU. */
-int gf_attention_tuning(int impl, int emu_pairs);
 
 /* Patch gather for the (1,2,2) Conv3d patch embedding (wan_video_dit.py:307-308,341-349; ControlNet
  * src/goal_force/wan_video_new.py:83,91-92).  Reads channels of up to two NCTHW tensors (the torch.cat([x, y]) at
@@ -96,6 +105,10 @@ int gf_unpatchify_bf16(const void* tokens, long long ldt, void* out, int C, int 
 
 /* y[i, :] = a[i, :] + b[:]  (bf16 add with one rounding; modulation + t_mod, wan_video_dit.py:218-219,264-267). */
 int gf_add_rows_bf16(const void* a, const void* b, void* y, int rows, int cols, void* stream);
+
+/* y = a + b elementwise, n bf16 elements, one rounding; y may alias a or b.  The strided ControlNet inject
+ * `x = x + states[i // stride]` (src/goal_force/wan_video_new.py:1559-1563). */
+int gf_add_bf16(const void* a, const void* b, void* y, long long n, void* stream);
 
 /* y = silu(x) elementwise (time_projection.0, wan_video_dit.py:319-320). */
 int gf_silu_bf16(const void* x, void* y, long long n, void* stream);
@@ -131,15 +144,22 @@ int gf_ulysses_unpack_bf16(const void* in, void* y, long long ldy, int rows, int
  * gf_peer_alloc: zero-filled device buffer that other processes of the node may map (cudaMalloc + CUDA IPC).
  * gf_peer_export / gf_peer_import: 64-byte handle of such a buffer / mapping of a peer's handle into this process
  * (the host side exchanges the handles, e.g. with torch.distributed.all_gather_object).
- * gf_peer_barrier: flag_peers[r] = rank r's flag buffer (>= 4*n_peers bytes, zero at start; own buffer at [rank]).
- * Enqueues a kernel that publishes this rank's earlier writes, signals `epoch` to every peer and waits until every
- * peer has signalled `epoch`; epochs must increase by one per call, identically on all ranks. */
+ * gf_peer_barrier: flag_peers[r] = rank r's flag buffer (>= 256 bytes, zero at start; own buffer at [rank]).
+ * Enqueues a kernel that publishes this rank's earlier writes, signals the next epoch to every peer and waits until
+ * every peer has signalled it.  The epoch counter lives in the flag buffer (so the call can be captured in a CUDA
+ * graph); all ranks must issue the same sequence of barriers.  The wait is bounded by wall-clock time: if a peer
+ * does not arrive within timeout_ms (<= 0: 60 s) the kernel stores 1 + peer index into *status (device pointer from
+ * gf_peer_status_alloc, may be NULL) and returns -- no trap; the host polls the mapped word and raises.
+ * gf_peer_status_alloc: 64 bytes of zeroed host-mapped memory; *host_ptr for the CPU, *dev_ptr for the kernels. */
 int gf_peer_alloc(void** ptr, long long bytes);
 int gf_peer_free(void* ptr);
 int gf_peer_export(void* ptr, void* handle64);
 int gf_peer_import(const void* handle64, void** ptr);
 int gf_peer_unimport(void* ptr);
-int gf_peer_barrier(void* const* flag_peers, int n_peers, int rank, unsigned epoch, void* stream);
+int gf_peer_barrier(void* const* flag_peers, int n_peers, int rank, long long timeout_ms, unsigned* status,
+                    void* stream);
+int gf_peer_status_alloc(unsigned** host_ptr, unsigned** dev_ptr);
+int gf_peer_status_free(unsigned* host_ptr);
 
 /* q/k RMSNorm + RoPE (as gf_qk_rmsnorm_rope_bf16) and v pass-through, written into the Ulysses receive buffers:
  * rank p owns heads [p*heads/P, (p+1)*heads/P), w = heads/P*head_dim columns.  Row r of this rank (global token
@@ -152,7 +172,7 @@ int gf_qkv_rmsnorm_rope_scatter_bf16(const void* qkv, long long ld, int rows, in
 /* gf_attention_bf16 whose output rows go back to their owners: global query row g belongs to rank g / rows_per_peer
  * and is stored at O_peers[g / rows_per_peer] + (g % rows_per_peer)*ldo + col_offset + head*head_dim
  * (col_offset = rank * heads * head_dim: this rank's head group inside the owner's [rows, all heads] buffer). */
-int gf_attention_scatter_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+int gf_attention_scatter_bf16(gf_ctx* ctx, const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
                               void* const* O_peers, int n_peers, long long ldo, int rows_per_peer, int col_offset,
                               int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
 

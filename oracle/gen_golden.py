@@ -154,18 +154,79 @@ def gen_control_channels():
     (GOLDEN / "control_channels.json").write_text(json.dumps(res, indent=1))
 
 
+class _FakeImage:
+    """Stands in for the PIL image the reference unit receives: .resize((w, h)) returns itself."""
+
+    def __init__(self, seed):
+        self.seed = seed
+
+    def resize(self, size):
+        self.size = size
+        return self
+
+
+class _FakePipe:
+    """The attributes WanVideoUnit_ImageEmbedderVAE.process touches (src/goal_force/wan_video_new.py:894-917); the VAE
+    is replaced by a seeded random latent generator -- the mask / concat bookkeeping under test is the reference's."""
+
+    def __init__(self):
+        import types
+        self.device, self.torch_dtype = "cpu", torch.bfloat16
+        self.dit = types.SimpleNamespace(require_vae_embedding=True)
+        self.vae = types.SimpleNamespace(encode=self._encode)
+
+    def load_models_to_device(self, names):
+        pass
+
+    def preprocess_image(self, img):
+        w, h = img.size
+        g = torch.Generator("cpu").manual_seed(img.seed)
+        return torch.rand(1, 3, h, w, generator=g) * 2 - 1
+
+    def _encode(self, videos, device=None, tiled=False, tile_size=None, tile_stride=None):
+        v = videos[0]                                  # (3, num_frames, H, W)
+        self.vae_input_digest = CC.digest(v.to(torch.bfloat16))
+        g = torch.Generator("cpu").manual_seed(77)
+        return [torch.randn(16, (v.shape[1] - 1) // 4 + 1, v.shape[2] // 8, v.shape[3] // 8, generator=g)]
+
+
+def vae_latents_for_mask_golden(num_frames, height, width):
+    g = torch.Generator("cpu").manual_seed(77)
+    return torch.randn(16, (num_frames - 1) // 4 + 1, height // 8, width // 8, generator=g)
+
+
+def gen_mask(ns):
+    """a21: y = cat(mask, vae_latents) exactly as the reference unit builds it (incl. the end-image variant)."""
+    unit = ns.pipe_mod.WanVideoUnit_ImageEmbedderVAE()
+    out = {}
+    for name, (nf, h, w, end) in {"small": (81, 64, 96, False), "small_end": (81, 64, 96, True),
+                                  "odd_frames": (17, 32, 48, False), "full": (81, 480, 832, False)}.items():
+        pipe = _FakePipe()
+        r = unit.process(pipe, _FakeImage(1), _FakeImage(2) if end else None, nf, h, w, True, (30, 52), (15, 26))
+        y = r["y"]
+        assert y.dtype == torch.bfloat16 and y.shape == (1, 20, (nf - 1) // 4 + 1, h // 8, w // 8)
+        ent = dict(num_frames=nf, height=h, width=w, end_image=end, digest=CC.digest(y))
+        if name != "full":
+            ent["y"] = y
+        out[name] = ent
+        print("mask", name, tuple(y.shape), ent["digest"])
+    torch.save(out, GOLDEN / "image_condition.pt")
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     ns = ref_shim.load()
     import sys
-    what = sys.argv[1:] or ["scheduler", "dit", "control"]
+    what = sys.argv[1:] or ["scheduler", "dit", "control", "mask"]
     if "scheduler" in what:
         gen_scheduler(ns)
     if "dit" in what:
         gen_dit(ns)
     if "control" in what:
         gen_control_channels()
+    if "mask" in what:
+        gen_mask(ns)
 
 
 if __name__ == "__main__":

@@ -78,6 +78,24 @@ def test_first_frame_mask_and_condition():
     assert latent_shape(81, 480, 832) == (1, 16, 21, 60, 104)
 
 
+def test_image_condition_matches_reference_unit_golden(golden_dir):
+    """a21: y = cat(mask, vae_latents)[None] is bit-identical to what the reference's WanVideoUnit_ImageEmbedderVAE
+    (src/goal_force/wan_video_new.py:887-917) builds, incl. the end-image variant and a 17-frame clip; vectors come
+    from oracle/gen_golden.py::gen_mask, which runs the reference unit itself (VAE stubbed by seeded latents)."""
+    g = torch.load(golden_dir / "image_condition.pt", weights_only=False)
+    assert set(g) == {"small", "small_end", "odd_frames", "full"}
+    for name, e in g.items():
+        gen = torch.Generator("cpu").manual_seed(77)
+        lat = torch.randn(16, (e["num_frames"] - 1) // 4 + 1, e["height"] // 8, e["width"] // 8, generator=gen)
+        y = image_condition(lat.to(torch.bfloat16), e["num_frames"], end_image=e["end_image"])
+        assert y.dtype == torch.bfloat16
+        assert CC.digest(y) == e["digest"], name
+        if "y" in e:
+            assert torch.equal(y, e["y"]), name
+            m = first_frame_mask(e["num_frames"], e["height"] // 8, e["width"] // 8, e["end_image"])
+            assert torch.equal(m.to(torch.bfloat16), e["y"][0, :4]), name
+
+
 def test_generate_noise_is_seed_reproducible_on_cpu():
     a = generate_noise((1, 16, 2, 4, 4), seed=5, device="cpu")
     g = torch.Generator("cpu").manual_seed(5)
@@ -155,3 +173,69 @@ def test_from_reference_modules_weight_layout():
     assert (cn.cfg.dim, cn.cfg.num_heads, cn.cfg.ffn_dim, cn.num_layers, cn.stride) == (5120, 40, 13824, 1, None)
     assert cn.is_noop                                          # zero_module(...) convs: branch is an exact no-op
     assert cn.patch_w.shape == (5120, 64) and cn.zero_w[0].shape == (5120, 5120)
+
+
+@pytest.mark.reference
+def test_standins_mirror_live_reference():
+    """oracle/ref_standins.py (used on the GPU box, where /root/reference is absent) has the reference's state_dict keys,
+    shapes and the attribute surface goal_force_b200 reads."""
+    from oracle import ref_shim
+    from oracle import ref_standins as S
+    ns = ref_shim.load()
+    cfg = O.DiTConfig(dim=256, in_dim=36, ffn_dim=512, out_dim=16, text_dim=64, freq_dim=256, eps=1e-6, num_heads=2,
+                      num_layers=2)
+    ref = ns.WanModel(**ref_shim.cfg_kwargs(cfg))
+    mine = S.wan_standin_from_cfg(cfg, dtype=torch.float32)
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs) == list(ms)
+    assert all(rs[k].shape == ms[k].shape for k in rs)
+    for a in ("dim", "in_dim", "freq_dim", "has_image_input", "seperated_timestep", "require_vae_embedding",
+              "require_clip_embedding", "fuse_vae_embedding_in_latents", "has_image_pos_emb", "has_ref_conv",
+              "control_adapter"):
+        assert getattr(ref, a) == getattr(mine, a), a
+    assert tuple(ref.patch_size) == tuple(mine.patch_size)
+    rb, mb = ref.blocks[0], mine.blocks[0]
+    assert (rb.dim, rb.num_heads, rb.ffn_dim, rb.norm1.eps) == (mb.dim, mb.num_heads, mb.ffn_dim, mb.norm1.eps)
+    assert ref.head.head.out_features == mine.head.head.out_features
+    assert ref.text_embedding[0].in_features == mine.text_embedding[0].in_features
+    cn_ref = ns.ControlNet(1, torch_dtype=torch.bfloat16)
+    cn = S.ControlNetStandIn(1)
+    crs, cms = cn_ref.state_dict(), cn.state_dict()
+    assert list(crs) == list(cms)
+    assert all(crs[k].shape == cms[k].shape and crs[k].dtype == cms[k].dtype for k in crs)
+    assert (cn_ref.num_layers, cn_ref.stride) == (cn.num_layers, cn.stride)
+    b0, m0 = cn_ref.controlnet_dit.blocks[0], cn.controlnet_dit.blocks[0]
+    assert (b0.dim, b0.num_heads, b0.ffn_dim, b0.norm1.eps) == (m0.dim, m0.num_heads, m0.ffn_dim, m0.norm1.eps)
+
+
+def test_conversion_cache_tracks_weight_changes(monkeypatch):
+    """a reference module converted once must be re-converted when its weights change (load_state_dict /
+    LoRA merge / load_controlnet_weights after a warm-up call), is_noop must follow, unsupported variants raise, and
+    the cache must not keep the reference module alive."""
+    import gc
+    import weakref
+    from goal_force_b200 import wan_dit as W
+    from oracle import ref_standins as S
+    monkeypatch.setattr(W, "_module_device", lambda m: torch.device("cpu"))
+    monkeypatch.setattr(W.capi, "load", lambda: None)
+    cfg = O.DiTConfig(dim=256, in_dim=36, ffn_dim=512, out_dim=16, text_dim=64, freq_dim=256, eps=1e-6, num_heads=2,
+                      num_layers=1)
+    cn = S.controlnet_standin_from_cfg(cfg, 1)
+    # head_dim must be 128 for the kernels: dim 256 / 2 heads
+    a = W._as_b200(cn, W.ControlNetB200)
+    assert a.is_noop and W._as_b200(cn, W.ControlNetB200) is a            # cached while the weights are unchanged
+    with torch.no_grad():
+        cn.controlnet_zero_convs_after[0].weight.add_(0.01)               # what load_controlnet_weights does
+    b = W._as_b200(cn, W.ControlNetB200)
+    assert b is not a and not b.is_noop
+    cn.load_state_dict({k: torch.zeros_like(v) for k, v in cn.state_dict().items()})
+    assert W._as_b200(cn, W.ControlNetB200).is_noop
+    ref = weakref.ref(cn)
+    key = id(cn)
+    del cn
+    gc.collect()
+    assert ref() is None and key not in W._CONVERTED                      # the cache holds the module only weakly
+    dit = S.wan_standin_from_cfg(cfg)
+    dit.seperated_timestep = True
+    with pytest.raises(NotImplementedError, match="seperated_timestep"):
+        W.WanModelB200.from_reference(dit, device="cpu")

@@ -126,10 +126,10 @@ def _attn_ref(q, k, v, heads):
 
 @pytest.fixture(params=[(80, 0), (80, 4), (128, 4), (128, 0)], ids=lambda p: f"impl{p[0]}-emu{p[1]}")
 def attn_variant(capi, request):
-    """every attention kernel variant selectable through gf_attention_tuning; the default is restored afterwards"""
+    """every attention kernel variant selectable through gf_ctx_set_attention; the default is restored afterwards"""
     capi.attention_tuning(*request.param)
     yield request.param
-    capi.attention_tuning(80, 0)        # (a forced choice stays forced for the rest of the process; 80/0 is the default kernel)
+    capi.attention_tuning(0, -1)        # back to the per-shape default
 
 
 @pytest.mark.parametrize("Lq,Lk,heads,amp", [(256, 128, 1, 1.0), (1, 7, 1, 1.0), (300, 200, 2, 1.0), (512, 1024, 3, 1.0),

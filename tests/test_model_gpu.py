@@ -4,7 +4,7 @@
 
 Tolerance (BASELINE.json: per-step bf16 output relative L2 <= 1e-2 against the reference forward; SURVEY F15: the
 reference's own bf16 forward is 1.55e-2 away from its fp32 forward at config 1, so a bf16 implementation cannot be
-held to 1e-2 against fp32):   relL2(ours, ref_fp32) <= max(1e-2, 1.1 * relL2(ref_bf16, ref_fp32)).
+held to 1e-2 against fp32):   relL2(ours, ref_fp32) <= max(1e-2, 1.0 * relL2(ref_bf16, ref_fp32)).
 """
 import pytest
 import torch
@@ -70,7 +70,7 @@ def _check(out, ref32, refbf):
     e_bf = O.rel_l2(out, refbf)
     print(f"relL2 ours-vs-fp32 {e_ours:.3e}  ref_bf16-vs-fp32 {e_ref:.3e}  ours-vs-ref_bf16 {e_bf:.3e}")
     assert not torch.isnan(out).any()
-    assert e_ours <= max(TOL_ABS, 1.1 * e_ref), (e_ours, e_ref)
+    assert e_ours <= max(TOL_ABS, 1.0 * e_ref), (e_ours, e_ref)
     return e_ours, e_ref
 
 
