@@ -31,7 +31,44 @@ METRIC = "A14B DiT denoise steps/sec (81x480x832, 32760 tokens, goal-force Contr
 UNIT = "steps/s"
 FRAMES_LAT, H_LAT, W_LAT = 21, 60, 104          # 81 x 480 x 832 video -> latent grid; tokens = 21*30*52 = 32760
 CONTROLNET_LAYERS = 10
-ATTN_DRAM_BYTES_PER_LAUNCH = 1.044257e9 + 319.568384e6     # ncu: dram read + write of gf_attn80_kernel, L = 32760, 40 heads
+
+
+def attn_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE gf_attn80_kernel launch at this shape (L = 32760, 40 heads),
+    parsed from the newest committed `ncu --set full` summary profiles/rNN_attn80_ncu.csv (units are in the header).
+    Returns (bytes, source) or (None, reason)."""
+    import csv
+    import re
+    cands = sorted((ROOT / "profiles").glob("r*_attn80_ncu.csv"), reverse=True)
+    for path in cands:
+        try:
+            rows = list(csv.reader(path.read_text().splitlines()))
+            head, row = rows[0], rows[1]
+            total = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                col = next(i for i, h in enumerate(head) if h.startswith(key))
+                unit = re.search(r"\[(\w+)\]", head[col]).group(1).lower()
+                mult = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
+                total += float(row[col]) * mult
+            return total, f"profiles/{path.name}"
+        except Exception:  # noqa: BLE001 - malformed file: try the next one
+            continue
+    return None, "no profiles/r*_attn80_ncu.csv"
+
+
+def gpu_reference_context():
+    """Context, not a target and not the reference arm: the reference algorithm as eager PyTorch + cuDNN attention on
+    the same kind of GPU, measured by tools/gpu_oracle_baseline.py and committed under profiles/."""
+    cands = sorted((ROOT / "profiles").glob("r*_gpu_eager_oracle.json"), reverse=True)
+    for path in cands:
+        try:
+            d = json.loads(path.read_text())
+            return {"what": d.get("what"), "ms_per_step": round(1000.0 * d["extrapolated_seconds_per_forward_50_blocks"], 1),
+                    "timed_blocks": d.get("timed_blocks"), "full_forward_measured": d.get("full_forward_measured", False),
+                    "source": f"profiles/{path.name}", "note": "committed measurement, not taken in this run"}
+        except Exception:  # noqa: BLE001
+            continue
+    return None
 
 
 def parse():
@@ -60,7 +97,9 @@ def peaks():
 
 
 def total_flops(L, d, ffn, ctx, layers):
-    per_block = 8 * L * d * d + 4 * L * L * d + 4 * L * d * d + 4 * ctx * d * d + 4 * L * ctx * d + 4 * L * d * ffn
+    """Work executed per step: self-attention linears + attention, cross-attention q/o linears + attention, FFN.  The
+    cross-attention K/V projections of the 512 context tokens are step-invariant and cached, so they are not counted."""
+    per_block = 8 * L * d * d + 4 * L * L * d + 4 * L * d * d + 4 * L * ctx * d + 4 * L * d * ffn
     return per_block * layers
 
 
@@ -111,44 +150,38 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
 def cpu_reference_sample(threads: int):
-    """Times the reference algorithm (oracle port, bit-identical to the reference's PyTorch code on CPU) on a bounded
-    sample of the config-2 forward and extrapolates to one full step:
-      * token-local part of one A14B DiTBlock (LayerNorms, q/k/v/o + RMSNorm + RoPE, cross-attention against 512
-        context tokens, FFN) on 8190 of the 32,760 tokens, scaled by 4;
-      * self-attention softmax(QK^T)V at the full 32,760 x 32,760 length for 8 of the 40 heads, scaled by 5;
-      * x 50 blocks (40 trunk + 10 ControlNet).  bf16, torch CPU kernels, all host threads.
-    Returns (steps_per_s, seconds_measured, description)."""
+    """Times the reference algorithm (oracle port, bit-identical to the reference's PyTorch code on CPU) on ONE full
+    A14B DiTBlock at the full config-2 length -- 32,760 tokens, all 40 heads: LayerNorms, q/k/v/o + RMSNorm + complex128
+    RoPE, full-length self-attention, cross-attention against 512 context tokens, FFN -- exactly as SURVEY 8(d)
+    prescribes (no token or head sub-sampling).  One step = 50 such blocks (40 trunk + 10 ControlNet; the patch embed,
+    head and zero-conv GEMMs, < 1 % of the work, are left out), so steps/s = 1 / (50 x t_block), labelled extrapolated.
+    bf16, torch CPU kernels, all host threads.  Returns (steps_per_s, seconds_measured, description)."""
     import torch
     from oracle import wan_dit_oracle as O
     torch.set_num_threads(threads)
     cfg = O.DiTConfig(**{**O.WAN22_I2V_A14B.__dict__, "num_layers": 1})
     L = FRAMES_LAT * (H_LAT // 2) * (W_LAT // 2)
-    Ls, heads_s = 8190, 8
     g = torch.Generator("cpu").manual_seed(0)
     sd = {}
     rn = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale)  # noqa: E731
     O._random_block(sd, "blocks.0", cfg, rn,
                     lambda n, o, i: sd.update({n + ".weight": rn(o, i, scale=i ** -0.5), n + ".bias": rn(o, scale=0.02)}))
     sd = {k: v.to(torch.bfloat16) for k, v in sd.items()}
-    x = torch.randn(1, Ls, cfg.dim, generator=g).bfloat16()
+    x = torch.randn(1, L, cfg.dim, generator=g).bfloat16()
     ctx = torch.randn(1, 512, cfg.dim, generator=g).bfloat16()
     t_mod = torch.randn(1, 6, cfg.dim, generator=g).bfloat16()
-    freqs = O.rope_freqs(cfg.head_dim, 21, 30, 52, "cpu")[:Ls]
-    q = torch.randn(1, L, heads_s * 128, generator=g).bfloat16()
+    freqs = O.rope_freqs(cfg.head_dim, FRAMES_LAT, H_LAT // 2, W_LAT // 2, "cpu")
     with torch.no_grad():
         O.dit_block(sd, "blocks.0", x[:, :64], ctx, t_mod, freqs[:64], cfg)           # warm-up (thread pool, caches)
         t0 = time.perf_counter()
         O.dit_block(sd, "blocks.0", x, ctx, t_mod, freqs, cfg)
-        t_tok = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        O.attention(q, q, q, heads_s)
-        t_att = time.perf_counter() - t0
+        t_block = time.perf_counter() - t0
     blocks = 40 + CONTROLNET_LAYERS
-    t_step = blocks * (t_tok * (L / Ls) + t_att * (40 / heads_s))
-    desc = (f"oracle port of the reference PyTorch CPU path, bf16, {threads} threads: one A14B DiTBlock token-local "
-            f"part on {Ls}/{L} tokens ({t_tok:.2f}s) + full-length self-attention for {heads_s}/40 heads "
-            f"({t_att:.2f}s), extrapolated x{L / Ls:.1f} tokens, x{40 // heads_s} heads, x{blocks} blocks")
-    return 1.0 / t_step, t_tok + t_att, desc
+    t_step = blocks * t_block
+    desc = (f"oracle port of the reference PyTorch CPU path, bf16, {threads} threads: ONE full A14B DiTBlock at "
+            f"{L} tokens x 40 heads measured ({t_block:.2f}s), EXTRAPOLATED x{blocks} blocks to one step "
+            f"(SURVEY 8(d)); embeddings/head/zero-convs (<1%) not included")
+    return 1.0 / t_step, t_block, desc
 
 
 def run_reference(args, emit):
@@ -156,17 +189,18 @@ def run_reference(args, emit):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    # each timed step is one bounded sample (one full-length DiTBlock); the warm-up is the small call inside the sample
+    # (thread pool / allocator), W full-length warm-up blocks would only burn minutes of host time
     vals, secs, desc = [], 0.0, ""
-    for i in range(max(1, args.warmup > 0) + args.steps):
+    for _ in range(max(1, args.steps)):
         v, s, desc = cpu_reference_sample(threads)
-        if i >= (1 if args.warmup > 0 else 0):
-            vals.append(v)
-            secs += s
-    value = sum(vals) / len(vals)
+        vals.append(v)
+        secs += s
+    value = len(vals) / sum(1.0 / v for v in vals)          # steps/s over the measured samples (harmonic mean)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "reference",
-            "config": workload_config(args, 1),
+            "config": workload_config(args, 1), "extrapolated": True, "seconds_measured": round(secs, 2),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -278,15 +312,17 @@ def run_ours(args, emit):
                                                                  if cn is not None else 0)
     att = kern.get("attention_self", {"launches": 0, "ms": 0.0, "work": 0.0})
     roof = None
+    traffic, traffic_src = attn_dram_traffic()
     if att["launches"]:
         ach = att["work"] / att["ms"] / 1e9
         roof = {"kernel": "gf_attn80_kernel (self-attention, tcgen05 flash attention)", "bound": "tensor",
                 "achieved": round(ach, 1), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops"], 4),
                 "peak_source": f"{pk['source']} (cuBLAS bf16 sustained, MEASURED_PEAKS.json)",
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, from the ncu --set full
-                # capture summarised in profiles/r01_attn80_ncu.csv (algorithmic Q+K+V+O = 1.342e9 bytes)
-                "traffic": ATTN_DRAM_BYTES_PER_LAUNCH if (world == 1 and args.layers > 0) else None,
-                "traffic_unit": "bytes/launch (ncu, profiles/r01_attn80_ncu.csv)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, parsed from the committed
+                # ncu --set full summary (algorithmic Q+K+V+O = 1.342e9 bytes)
+                "traffic": traffic if (world == 1 and args.layers > 0) else None,
+                "traffic_unit": f"bytes/launch (ncu, {traffic_src})",
+                "algorithmic_bytes_per_launch": 4.0 * L * cfg.dim * 2,
                 "launches": att["launches"], "avg_ms": round(att["ms"] / att["launches"], 4),
                 "share_of_step": round(att["ms"] / ms, 4),
                 "flops_per_launch": att["work"] / att["launches"]}
@@ -313,6 +349,9 @@ def run_ours(args, emit):
     if e2e is not None:
         line["e2e"] = {"value": round(1000.0 / (e2e / args.steps), 5), "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e / args.steps, 3)}
+    ctx_ref = gpu_reference_context()
+    if ctx_ref is not None and world == 1:
+        line["gpu_reference_context"] = ctx_ref
     if world == 1 and not args.no_cpu_baseline:
         v, _, desc = cpu_reference_sample(os.cpu_count() or 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc}

@@ -45,7 +45,7 @@ constexpr int A8_Q_BYTES = A8_BM * A8_D * 2;    // 32 KB per tile: two [128][64]
 constexpr int A8_QHALF = A8_BM * 64 * 2;        // 16 KB
 constexpr int A8_SLOT_BYTES = A8_BN * A8_D * 2; // 20 KB: two [80][64] boxes
 constexpr int A8_HALF = A8_BN * 64 * 2;         // 10 KB
-constexpr int A8_XCHG_BYTES = 2 * 2 * 2 * A8_BM * 4;  // [parity][tile][half][row] fp32 exchange slots
+constexpr int A8_XCHG_BYTES = 2 * 2 * 2 * A8_BM * 8;  // [parity][tile][half][row] 8-byte exchange slots {value, tag}
 constexpr int A8_SMEM_BYTES = 2 * A8_Q_BYTES + A8_SLOTS * A8_SLOT_BYTES + A8_XCHG_BYTES + 1024 + 256;
 constexpr float A8_RESCALE_THRESHOLD = 8.0f;    // log2 domain
 
@@ -57,7 +57,13 @@ struct Attn80Params {
   float scale_log2;      // softmax scale * log2(e)
 };
 
-template <int kEmuPairs>
+// kXchg: how the two threads of a query row exchange their half-row maxima every kv block
+//   0  one 256-thread named barrier per tile (all 8 softmax warps of the tile in lock-step)
+//   1  one 64-thread named barrier per warp pair (the two warps that share a TMEM lane quarter)
+//   2  no barrier: each thread publishes {value, block index} with one 8-byte shared store right after its row
+//      maximum is known, exponentiates speculatively, and only then reads the partner's slot (polling the tag; by
+//      then the value has practically always arrived), so the warps of a tile never wait for each other
+template <int kEmuPairs, int kXchg>
 __global__ void __launch_bounds__(A8_THREADS, 1)
 gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const Attn80Params p) {
@@ -113,6 +119,10 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     __syncwarp();
     tmem_alloc<1>(tmem_ptr_smem, 512);
     tmem_relinquish<1>();
+  }
+  if constexpr (kXchg == 2) {
+    for (int t = threadIdx.x; t < A8_XCHG_BYTES / 8; t += A8_THREADS)
+      asm volatile("st.shared.b64 [%0], %1;" ::"r"(xchg_smem + 8u * t), "l"(0xFFFFFFFF00000000ull) : "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -226,20 +236,38 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int row = q0 + i * A8_BM + r;
     const int tail_valid = p.Lk - (n_kv - 1) * A8_BN - hf * A8_HC;   // valid columns of this half in the last block
     const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
-    const uint32_t x_mine = xchg_smem + uint32_t(((i * 2 + hf) * A8_BM + r) * 4);
-    const uint32_t x_other = xchg_smem + uint32_t(((i * 2 + (hf ^ 1)) * A8_BM + r) * 4);
-    const uint32_t pair_bar = 1 + i;                 // named barrier of the tile's 256 softmax threads
+    const uint32_t x_mine = xchg_smem + uint32_t(((i * 2 + hf) * A8_BM + r) * 8);
+    const uint32_t x_other = xchg_smem + uint32_t(((i * 2 + (hf ^ 1)) * A8_BM + r) * 8);
+    const uint32_t tile_bar = 1 + i;                 // named barrier of the tile's 256 softmax threads
+    const uint32_t pair_bar = 3 + i * 4 + wq;        // named barrier of the two warps sharing this lane quarter
     float m_used = 0.f, l = 0.f;
 
-    // Value held by the thread owning the other half of the row.  Slots alternate with `parity` so that a
-    // thread's next write can never overtake its partner's read of the previous one.
-    auto exchange = [&](float mine, int parity) -> float {
-      const uint32_t off = uint32_t(parity & 1) * (A8_XCHG_BYTES / 2);
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_mine + off), "f"(mine) : "memory");
-      named_bar_sync(pair_bar, 256);
-      float other;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(x_other + off) : "memory");
-      return other;
+    // Value held by the thread owning the other half of the row.  Slots alternate with the parity of `tag` so that
+    // a thread's next write can never overtake its partner's read of the previous one (a thread can be at most one
+    // kv block ahead of its partner: storing P(j+1) needs PV(j), which needs the partner's P(j)).
+    auto publish = [&](float mine, int tag) {
+      const uint32_t off = uint32_t(tag & 1) * (A8_XCHG_BYTES / 2);
+      if constexpr (kXchg == 2) {
+        const uint64_t v = (uint64_t(uint32_t(tag)) << 32) | uint64_t(__float_as_uint(mine));
+        asm volatile("st.volatile.shared.b64 [%0], %1;" ::"r"(x_mine + off), "l"(v) : "memory");
+      } else {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_mine + off), "f"(mine) : "memory");
+      }
+    };
+    auto collect = [&](int tag, bool whole_tile) -> float {
+      const uint32_t off = uint32_t(tag & 1) * (A8_XCHG_BYTES / 2);
+      if constexpr (kXchg == 2) {
+        uint64_t v;
+        do {
+          asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(v) : "r"(x_other + off) : "memory");
+        } while (uint32_t(v >> 32) != uint32_t(tag));
+        return __uint_as_float(uint32_t(v));
+      } else {
+        if (kXchg == 0 || whole_tile) named_bar_sync(tile_bar, 256); else named_bar_sync(pair_bar, 64);
+        float other;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(x_other + off) : "memory");
+        return other;
+      }
     };
 
     auto kv_block = [&](const int j, auto first_tag) {
@@ -263,7 +291,8 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (32 + k >= tail_valid) s1[k] = 0xFF800000u;
       }
       const float hmax = fmaxf(cols_max<32>(s0), cols_max<8>(s1));
-      if constexpr (kFirst) m_used = fmaxf(hmax, exchange(hmax, j)) * p.scale_log2;
+      publish(hmax, j);
+      if constexpr (kFirst) m_used = fmaxf(hmax, collect(j, false)) * p.scale_log2;
       uint64_t acc[2] = {0ull, 0ull};
       uint32_t pk0[16], pk1[4];
       {
@@ -273,7 +302,7 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       if constexpr (!kFirst) {
         // true row max of this block (log2 domain); both threads of the row see the same value
-        const float m_cur = fmaxf(hmax, exchange(hmax, j)) * p.scale_log2;
+        const float m_cur = fmaxf(hmax, collect(j, false)) * p.scale_log2;
         // PV(j-1, i) must have drained P (and, for a rescale, O) before either is written
         mbar_wait(p_free(i), (j - 1) & 1);
         tc_fence_after();
@@ -315,7 +344,8 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int j = 1; j < n_kv; ++j) kv_block(j, std::false_type{});
 
     // ---------------- epilogue: O / l -> bf16 -> global (this thread: 64 of the row's 128 columns)
-    const float inv_l = 1.0f / (l + exchange(l, n_kv));
+    publish(l, n_kv);
+    const float inv_l = 1.0f / (l + collect(n_kv, true));
     mbar_wait(p_free(i), (n_kv - 1) & 1);
     tc_fence_after();
     __nv_bfloat16* orow;
@@ -352,10 +382,10 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
-template <int kEmuPairs>
+template <int kEmuPairs, int kXchg>
 static int launch80(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const Attn80Params& p,
                     cudaStream_t stream) {
-  auto kern = gf_attn80_kernel<kEmuPairs>;
+  auto kern = gf_attn80_kernel<kEmuPairs, kXchg>;
   static bool configured[64] = {};
   if (int rc = gf_set_smem_once(configured, reinterpret_cast<const void*>(kern), A8_SMEM_BYTES)) return rc;
   const int items = p.q_blocks * p.heads;
@@ -364,7 +394,7 @@ static int launch80(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtens
 }
 
 int gf_attention80_launch(gf_ctx* ctx, const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
-                          const AttnOut& out, int Lq, int Lk, int heads, float scale, int emu_pairs,
+                          const AttnOut& out, int Lq, int Lk, int heads, float scale, int emu_pairs, int xchg,
                           cudaStream_t stream) {
   CUtensorMap scr[3];
   int rc = 0;
@@ -383,11 +413,19 @@ int gf_attention80_launch(gf_ctx* ctx, const void* Q, long long ldq, const void*
   const int tail = sms > 0 ? items % sms : 0;
   p.n_full = (tail > 0 && items > sms && 2 * tail <= sms) ? items - tail : items;
   p.scale_log2 = scale * 1.4426950408889634f;
-  switch (emu_pairs) {
-    case 0: return launch80<0>(*tmQ, *tmK, *tmV, p, stream);
-    case 2: return launch80<2>(*tmQ, *tmK, *tmV, p, stream);
-    case 6: return launch80<6>(*tmQ, *tmK, *tmV, p, stream);
-    default: return launch80<4>(*tmQ, *tmK, *tmV, p, stream);
+  auto go = [&](auto xtag) -> int {
+    constexpr int kX = decltype(xtag)::value;
+    switch (emu_pairs) {
+      case 0: return launch80<0, kX>(*tmQ, *tmK, *tmV, p, stream);
+      case 2: return launch80<2, kX>(*tmQ, *tmK, *tmV, p, stream);
+      case 6: return launch80<6, kX>(*tmQ, *tmK, *tmV, p, stream);
+      default: return launch80<4, kX>(*tmQ, *tmK, *tmV, p, stream);
+    }
+  };
+  switch (xchg) {
+    case 0: return go(std::integral_constant<int, 0>{});
+    case 1: return go(std::integral_constant<int, 1>{});
+    default: return go(std::integral_constant<int, 2>{});
   }
 }
 

@@ -422,11 +422,62 @@ def g_attn_sweep():
     return res
 
 
+def g_attn_ab():
+    """Same-process, same-box A/B of attention kernel variants at the config-2 self-attention shape
+    (GF_ATTN_AB = "impl:emu,impl:emu,..."): accuracy on the rescale / ragged cases, then burst and sustained timings,
+    visiting the variants round-robin twice so that thermal drift hits all of them alike; cuDNN SDPA beside it."""
+    import torch
+    import torch.nn.functional as F
+    from goal_force_b200 import capi
+    variants = [tuple(int(x) for x in v.split(":")) for v in
+                os.environ.get("GF_ATTN_AB", "80:0,81:0,82:0,80:2,81:2,82:2,82:4").split(",")]
+    heads, d, L = 40, 5120, 32760
+    torch.manual_seed(0)
+    res = {}
+    q2 = torch.randn(1000, 2 * 128, device="cuda").bfloat16()
+    k2 = (torch.randn(1333, 2 * 128, device="cuda") * torch.linspace(0.2, 6.0, 1333, device="cuda")[:, None]).bfloat16()
+    v2 = torch.randn(1333, 2 * 128, device="cuda").bfloat16()
+    q3 = (torch.randn(300, 128, device="cuda") * 3).bfloat16()
+    k3 = (torch.randn(200, 128, device="cuda") * 3).bfloat16()
+    v3 = torch.randn(200, 128, device="cuda").bfloat16()
+    qa = torch.randn(4096, 3 * d, device="cuda").bfloat16()
+    refs = (_attn_ref(q2, k2, v2, 2), _attn_ref(q3, k3, v3, 1), _attn_ref(qa[:, :d], qa[:, d:2 * d], qa[:, 2 * d:], heads))
+    for impl, emu in variants:
+        capi.attention_tuning(impl, emu)
+        key = f"{impl}:{emu}"
+        res[key] = {"acc_rescale": _stats(capi.attention(q2, k2, v2, 2), refs[0])["rel_l2"],
+                    "acc_ragged": _stats(capi.attention(q3, k3, v3, 1), refs[1])["rel_l2"],
+                    "acc_L4096": _stats(capi.attention(qa[:, :d], qa[:, d:2 * d], qa[:, 2 * d:], heads), refs[2])["rel_l2"],
+                    "burst": [], "sustained": []}
+        print(key, res[key], flush=True)
+    qkv = torch.randn(L, 3 * d, device="cuda").bfloat16()
+    o = torch.empty(L, d, device="cuda", dtype=torch.bfloat16)
+    fl = 4.0 * L * L * d
+    run = lambda: capi.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], heads, out=o)  # noqa: E731
+    q4, k4, v4 = (qkv[:, i * d:(i + 1) * d].reshape(1, L, heads, 128).transpose(1, 2) for i in range(3))
+    sd = lambda: F.scaled_dot_product_attention(q4, k4, v4)  # noqa: E731
+    res["cudnn_sdpa"] = {"burst": [], "sustained": []}
+    for rnd in range(2):
+        for impl, emu in variants:
+            capi.attention_tuning(impl, emu)
+            key = f"{impl}:{emu}"
+            torch.cuda.synchronize(); time.sleep(0.5)
+            res[key]["burst"].append(round(fl / timed(run, iters=3, warmup=1) / 1e9, 1))
+            res[key]["sustained"].append(round(fl / timed(run, iters=60, warmup=0) / 1e9, 1))
+            print(key, "burst", res[key]["burst"], "sustained", res[key]["sustained"], flush=True)
+        torch.cuda.synchronize(); time.sleep(0.5)
+        res["cudnn_sdpa"]["burst"].append(round(fl / timed(sd, iters=3, warmup=1) / 1e9, 1))
+        res["cudnn_sdpa"]["sustained"].append(round(fl / timed(sd, iters=60, warmup=0) / 1e9, 1))
+        print("cudnn_sdpa", res["cudnn_sdpa"], flush=True)
+    capi.attention_tuning(0, -1)
+    return res
+
+
 GROUPS = {
     "gemm_small": g_gemm_small, "gemm_small2": g_gemm_small2, "gemm_epi": g_gemm_epi, "rowwise": g_rowwise,
     "misc": g_misc, "attn_small": g_attn_small, "gemm_perf": g_gemm_perf, "attn_perf": g_attn_perf,
     "rowwise_perf": g_rowwise_perf, "attn_one": g_attn_one, "attn_sweep": g_attn_sweep,
-    "gemm_sustained": g_gemm_sustained,
+    "gemm_sustained": g_gemm_sustained, "attn_ab": g_attn_ab,
 }
 
 
