@@ -26,8 +26,7 @@ const CUtensorMap* gf_ctx_tmap(gf_ctx* ctx, CUtensorMap* scratch, const void* ba
 
 // Per-context tuning (0 / negative = library default).
 struct CtxTuning {
-  int attn_impl = 0;       // 0: per shape (80 for long key sequences, 128 for Lk <= 1024); 80 / 128: forced;
-                           // 81 / 82: impl 80 with the half-row exchange variant 1 / 2 (gf_attn80.cu kXchg)
+  int attn_impl = 0;       // 0: per shape (80 for long key sequences, 128 for Lk <= 1024); 80 / 128: forced
   int attn_emu = -1;       // -1: kernel default; 0, 2, 4, 6: column pairs per 16 with exp2 on the FMA pipe
   int gemm_group_m = 0;    // 0: per shape; > 0: rasterisation group height in m-tiles
 };
@@ -57,7 +56,7 @@ struct AttnOut {
 
 // gf_attn80.cu: the decoupled 80-row-block attention kernel behind gf_attention_bf16 (arguments as the C ABI).
 int gf_attention80_launch(gf_ctx* ctx, const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
-                          const AttnOut& out, int Lq, int Lk, int heads, float scale, int emu_pairs, int xchg,
+                          const AttnOut& out, int Lq, int Lk, int heads, float scale, int emu_pairs,
                           cudaStream_t stream);
 
 }  // namespace gf

@@ -325,14 +325,9 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 //               -1 = kernel default (0 for impl 80, 4 for impl 128)
 // Short key sequences (cross-attention against 512 context tokens) are a handful of kv blocks per CTA: there the
 // 128-row-block kernel wastes fewer padded columns (512 = 4 x 128 vs 7 x 80) and measures ~8 % faster.
-constexpr int kDefaultXchg = 0;
 static int attn_impl_for(const CtxTuning& t, int Lk) {
   if (t.attn_impl == 80 || t.attn_impl == 128) return t.attn_impl;
-  if (t.attn_impl == 81 || t.attn_impl == 82) return 80;
   return Lk <= 1024 ? 128 : 80;
-}
-static int attn_xchg_for(const CtxTuning& t) {
-  return t.attn_impl == 81 ? 1 : (t.attn_impl == 82 ? 2 : (t.attn_impl == 80 ? 0 : kDefaultXchg));
 }
 static int attn_emu_for(const CtxTuning& t, int impl) { return t.attn_emu >= 0 ? t.attn_emu : (impl == 80 ? 0 : 4); }
 
@@ -362,8 +357,7 @@ static int attention_dispatch(gf_ctx* ctx, const void* Q, long long ldq, const v
   const CtxTuning tune = gf_ctx_tuning(ctx);
   const int impl = attn_impl_for(tune, Lk);
   const int emu = attn_emu_for(tune, impl);
-  if (impl == 80)
-    return gf_attention80_launch(ctx, Q, ldq, K, ldk, V, ldv, out, Lq, Lk, heads, scale, emu, attn_xchg_for(tune), s);
+  if (impl == 80) return gf_attention80_launch(ctx, Q, ldq, K, ldk, V, ldv, out, Lq, Lk, heads, scale, emu, s);
   CUtensorMap scr[3];
   int rc = 0;
   const CUtensorMap* tmQ = gf_ctx_tmap(ctx, &scr[0], Q, (uint64_t)heads * AT_D, (uint64_t)Lq, (uint64_t)ldq, 64, AT_BM, &rc);

@@ -45,11 +45,27 @@ constexpr int A8_Q_BYTES = A8_BM * A8_D * 2;    // 32 KB per tile: two [128][64]
 constexpr int A8_QHALF = A8_BM * 64 * 2;        // 16 KB
 constexpr int A8_SLOT_BYTES = A8_BN * A8_D * 2; // 20 KB: two [80][64] boxes
 constexpr int A8_HALF = A8_BN * 64 * 2;         // 10 KB
-constexpr int A8_XCHG_BYTES = 2 * 2 * 2 * A8_BM * 8;  // [parity][tile][half][row] 8-byte exchange slots {value, tag}
+constexpr int A8_XCHG_BYTES = 2 * 2 * 2 * A8_BM * 4;  // [parity][tile][half][row] fp32 exchange slots
 constexpr int A8_SMEM_BYTES = 2 * A8_Q_BYTES + A8_SLOTS * A8_SLOT_BYTES + A8_XCHG_BYTES + 1024 + 256;
 constexpr float A8_RESCALE_THRESHOLD = 8.0f;    // log2 domain
 
+// -DGF_A8_TRACE (experimental builds only, never the shipped library): CTA 0 records SM-clock timestamps of the
+// softmax / issuer phases of kv blocks [A8_TRACE_J0, A8_TRACE_J0 + A8_TRACE_NJ) into a global buffer set with
+// gf_debug_attn_trace(); layout [warp 0..19][block][8] of int64.
+#ifdef GF_A8_TRACE
+constexpr int A8_TRACE_J0 = 100, A8_TRACE_NJ = 32;
+static long long* g_a8_trace = nullptr;
+#define A8_TS(slot)                                                                                      \
+  do {                                                                                                   \
+    if (p.trace && blockIdx.x == 0 && lane_id() == 0 && j >= A8_TRACE_J0 && j < A8_TRACE_J0 + A8_TRACE_NJ) \
+      p.trace[((threadIdx.x >> 5) * A8_TRACE_NJ + (j - A8_TRACE_J0)) * 8 + (slot)] = clock64();           \
+  } while (0)
+#else
+#define A8_TS(slot) do { } while (0)
+#endif
+
 struct Attn80Params {
+  long long* trace;
   AttnOut out;
   int Lq, Lk, heads;
   int q_blocks;          // ceil(Lq / 256): two-tile work items per head
@@ -57,13 +73,7 @@ struct Attn80Params {
   float scale_log2;      // softmax scale * log2(e)
 };
 
-// kXchg: how the two threads of a query row exchange their half-row maxima every kv block
-//   0  one 256-thread named barrier per tile (all 8 softmax warps of the tile in lock-step)
-//   1  one 64-thread named barrier per warp pair (the two warps that share a TMEM lane quarter)
-//   2  no barrier: each thread publishes {value, block index} with one 8-byte shared store right after its row
-//      maximum is known, exponentiates speculatively, and only then reads the partner's slot (polling the tag; by
-//      then the value has practically always arrived), so the warps of a tile never wait for each other
-template <int kEmuPairs, int kXchg>
+template <int kEmuPairs>
 __global__ void __launch_bounds__(A8_THREADS, 1)
 gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const Attn80Params p) {
@@ -82,7 +92,10 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   auto p_free = [&](int i) { return bar_base + 8u * (7 + 2 * A8_SLOTS + i); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (9 + 2 * A8_SLOTS);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it
+  // (barrier addresses, TMEM addresses, MMA descriptors of the issuer warps) in uniform registers -- without it the
+  // issuers spend ~300 cycles per QK on R2UR moves and vector-register descriptor arithmetic
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   // Work items are (head, 256 query rows).  When the last, partial wave of items would leave most SMs idle, the host
   // splits those tail items into single-tile CTAs (`single`): tile 1's warps and issuer stay passive, and the tail
   // wave runs on twice as many SMs at roughly 0.6x the per-block time.
@@ -120,10 +133,6 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tmem_alloc<1>(tmem_ptr_smem, 512);
     tmem_relinquish<1>();
   }
-  if constexpr (kXchg == 2) {
-    for (int t = threadIdx.x; t < A8_XCHG_BYTES / 8; t += A8_THREADS)
-      asm volatile("st.shared.b64 [%0], %1;" ::"r"(xchg_smem + 8u * t), "l"(0xFFFFFFFF00000000ull) : "memory");
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -137,40 +146,46 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
    setmaxnreg_dec<A8_SERVICE_REGS>();
    if (warp == 16) {
     // ===================================================== TMA producer: Q, K0, then K(j+1), V(j) for every block
-    if (elect_one()) {
+    // (warp-wide loop for the same reason as the issuers; the elected lane issues the copies)
+    const bool lead = elect_one();
+    if (lead) {
       mbar_arrive_expect_tx(q_full, n_tiles * A8_Q_BYTES);
       for (int i = 0; i < n_tiles; ++i)
         for (int h = 0; h < 2; ++h)
           tma_load_2d(q_smem + i * A8_Q_BYTES + h * A8_QHALF, &tmQ, q_full, col0 + h * 64, q0 + i * A8_BM);
-      int slot = 0;
-      uint32_t phase = 0;
-      auto load = [&](const CUtensorMap* tm, int blk) {
-        mbar_wait(kv_empty(slot), phase ^ 1u);
+    }
+    int slot = 0;
+    uint32_t phase = 0;
+    auto load = [&](const CUtensorMap* tm, int blk) {
+      mbar_wait(kv_empty(slot), phase ^ 1u);
+      if (lead) {
         mbar_arrive_expect_tx(kv_full(slot), A8_SLOT_BYTES);
         for (int h = 0; h < 2; ++h)
           tma_load_2d(kv_smem + slot * A8_SLOT_BYTES + h * A8_HALF, tm, kv_full(slot), col0 + h * 64, blk * A8_BN);
-        if (++slot == A8_SLOTS) { slot = 0; phase ^= 1u; }
-      };
-      load(&tmK, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) load(&tmK, j + 1);
-        load(&tmV, j);
       }
+      __syncwarp();
+      if (++slot == A8_SLOTS) { slot = 0; phase ^= 1u; }
+    };
+    load(&tmK, 0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) load(&tmK, j + 1);
+      load(&tmV, j);
     }
    } else if (warp == 17 || warp == 18) {
     // ===================================================== MMA issuers: warp 17 drives tile 0, warp 18 tile 1
+    // The whole warp runs the loop (waits, ring bookkeeping) so that slot / phase / descriptors are warp-uniform and
+    // live in uniform registers; only the tcgen05 instructions themselves are issued by the elected lane.
+    const bool lead = elect_one();
     if (warp == 18 && single) {
       // passive tile: only keep the K/V ring turning (the slots are released by two arrivals)
-      if (elect_one()) {
-        int slot = 0;
-        uint32_t phase = 0;
-        for (int t = 0; t < 2 * n_kv; ++t) {
-          mbar_wait(kv_full(slot), phase);
-          mbar_arrive(kv_empty(slot));
-          if (++slot == A8_SLOTS) { slot = 0; phase ^= 1u; }
-        }
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < 2 * n_kv; ++t) {
+        mbar_wait(kv_full(slot), phase);
+        if (lead) mbar_arrive(kv_empty(slot));
+        if (++slot == A8_SLOTS) { slot = 0; phase ^= 1u; }
       }
-    } else if (elect_one()) {
+    } else {
       const int i = warp - 17;
       constexpr uint32_t idesc_qk = idesc_bf16(A8_BM, A8_BN, 0, 0);   // A = Q (K-major), B = K (K-major), N = 80
       constexpr uint32_t idesc_pv = idesc_bf16(A8_BM, A8_D, 0, 1);    // A = P (TMEM),    B = V (MN-major), N = 128
@@ -179,44 +194,55 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t qa = q_smem + i * A8_Q_BYTES;
       const uint32_t tS = tmem_S(i), tP = tmem_P(i), tO = tmem_O(i);
       const uint32_t sfull = s_full(i), sfree = s_free(i), pfull = p_full(i), pfree = p_free(i);
-      auto issue_qk = [&](uint32_t k_addr) {
+      auto issue_qk = [&](uint32_t k_addr, uint32_t release_bar) {
+        if (lead) {
 #pragma unroll
-        for (int kk = 0; kk < A8_D / 16; ++kk) {
-          const uint32_t qoff = (kk >> 2) * A8_QHALF + (kk & 3) * 32;
-          const uint32_t koff = (kk >> 2) * A8_HALF + (kk & 3) * 32;
-          umma_ss<1>(tS, smem_desc(desc_k, qa + qoff), smem_desc(desc_k, k_addr + koff), idesc_qk, kk != 0);
+          for (int kk = 0; kk < A8_D / 16; ++kk) {
+            const uint32_t qoff = (kk >> 2) * A8_QHALF + (kk & 3) * 32;
+            const uint32_t koff = (kk >> 2) * A8_HALF + (kk & 3) * 32;
+            umma_ss<1>(tS, smem_desc(desc_k, qa + qoff), smem_desc(desc_k, k_addr + koff), idesc_qk, kk != 0);
+          }
+          tc_commit(sfull);
+          tc_commit(release_bar);
         }
-        tc_commit(sfull);
+        __syncwarp();
       };
-      auto issue_pv = [&](uint32_t v_addr, bool first_block) {
+      auto issue_pv = [&](uint32_t v_addr, bool first_block, uint32_t release_bar) {
+        if (lead) {
 #pragma unroll
-        for (int kk = 0; kk < A8_BN / 16; ++kk)      // 16 kv rows per MMA: 8 packed-bf16 TMEM columns of P, 2 KB of V
-          umma_ts<1>(tO, tP + kk * 8, smem_desc(desc_v, v_addr + kk * 2048), idesc_pv,
-                     (first_block && kk == 0) ? 0u : 1u);
-        tc_commit(pfree);
+          for (int kk = 0; kk < A8_BN / 16; ++kk)    // 16 kv rows per MMA: 8 packed-bf16 TMEM columns of P, 2 KB of V
+            umma_ts<1>(tO, tP + kk * 8, smem_desc(desc_v, v_addr + kk * 2048), idesc_pv,
+                       (first_block && kk == 0) ? 0u : 1u);
+          tc_commit(pfree);
+          tc_commit(release_bar);
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       mbar_wait(kv_full(0), 0);
       tc_fence_after();
-      issue_qk(kv_smem);
-      tc_commit(kv_empty(0));
+      issue_qk(kv_smem, kv_empty(0));
       int slot = 1;                   // ring position of the next load (same sequence as the producer)
       uint32_t phase = 0;
       auto advance = [&]() { if (++slot == A8_SLOTS) { slot = 0; phase ^= 1u; } };
       for (int j = 0; j < n_kv; ++j) {
         if (j + 1 < n_kv) {
           mbar_wait(kv_full(slot), phase);
+          A8_TS(0);
           mbar_wait(sfree, j & 1);
+          A8_TS(1);
           tc_fence_after();
-          issue_qk(kv_smem + slot * A8_SLOT_BYTES);
-          tc_commit(kv_empty(slot));
+          issue_qk(kv_smem + slot * A8_SLOT_BYTES, kv_empty(slot));
+          A8_TS(2);
           advance();
         }
         mbar_wait(kv_full(slot), phase);
+        A8_TS(3);
         mbar_wait(pfull, j & 1);
+        A8_TS(4);
         tc_fence_after();
-        issue_pv(kv_smem + slot * A8_SLOT_BYTES, j == 0);
-        tc_commit(kv_empty(slot));
+        issue_pv(kv_smem + slot * A8_SLOT_BYTES, j == 0, kv_empty(slot));
+        A8_TS(5);
         advance();
       }
     }
@@ -236,48 +262,34 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int row = q0 + i * A8_BM + r;
     const int tail_valid = p.Lk - (n_kv - 1) * A8_BN - hf * A8_HC;   // valid columns of this half in the last block
     const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
-    const uint32_t x_mine = xchg_smem + uint32_t(((i * 2 + hf) * A8_BM + r) * 8);
-    const uint32_t x_other = xchg_smem + uint32_t(((i * 2 + (hf ^ 1)) * A8_BM + r) * 8);
+    const uint32_t x_mine = xchg_smem + uint32_t(((i * 2 + hf) * A8_BM + r) * 4);
+    const uint32_t x_other = xchg_smem + uint32_t(((i * 2 + (hf ^ 1)) * A8_BM + r) * 4);
     const uint32_t tile_bar = 1 + i;                 // named barrier of the tile's 256 softmax threads
-    const uint32_t pair_bar = 3 + i * 4 + wq;        // named barrier of the two warps sharing this lane quarter
     float m_used = 0.f, l = 0.f;
 
-    // Value held by the thread owning the other half of the row.  Slots alternate with the parity of `tag` so that
-    // a thread's next write can never overtake its partner's read of the previous one (a thread can be at most one
-    // kv block ahead of its partner: storing P(j+1) needs PV(j), which needs the partner's P(j)).
-    auto publish = [&](float mine, int tag) {
-      const uint32_t off = uint32_t(tag & 1) * (A8_XCHG_BYTES / 2);
-      if constexpr (kXchg == 2) {
-        const uint64_t v = (uint64_t(uint32_t(tag)) << 32) | uint64_t(__float_as_uint(mine));
-        asm volatile("st.volatile.shared.b64 [%0], %1;" ::"r"(x_mine + off), "l"(v) : "memory");
-      } else {
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_mine + off), "f"(mine) : "memory");
-      }
-    };
-    auto collect = [&](int tag, bool whole_tile) -> float {
-      const uint32_t off = uint32_t(tag & 1) * (A8_XCHG_BYTES / 2);
-      if constexpr (kXchg == 2) {
-        uint64_t v;
-        do {
-          asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(v) : "r"(x_other + off) : "memory");
-        } while (uint32_t(v >> 32) != uint32_t(tag));
-        return __uint_as_float(uint32_t(v));
-      } else {
-        if (kXchg == 0 || whole_tile) named_bar_sync(tile_bar, 256); else named_bar_sync(pair_bar, 64);
-        float other;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(x_other + off) : "memory");
-        return other;
-      }
+    // Value held by the thread owning the other half of the row.  Slots alternate with `parity` so that a
+    // thread's next write can never overtake its partner's read of the previous one.  (Measured alternatives that
+    // lost on the same box: a 64-thread barrier per warp pair, -1 %; a barrier-free tagged-slot poll, -1.5 %.)
+    auto exchange = [&](float mine, int parity) -> float {
+      const uint32_t off = uint32_t(parity & 1) * (A8_XCHG_BYTES / 2);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_mine + off), "f"(mine) : "memory");
+      named_bar_sync(tile_bar, 256);
+      float other;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(x_other + off) : "memory");
+      return other;
     };
 
     auto kv_block = [&](const int j, auto first_tag) {
       constexpr bool kFirst = decltype(first_tag)::value;
+      A8_TS(0);
       mbar_wait(s_full(i), j & 1);
+      A8_TS(1);
       tc_fence_after();
       uint32_t s0[32], s1[8];
       tmem_ld32(tS, s0);
       tmem_ld8(tS + 32, s1);
       tmem_ld_wait();
+      A8_TS(2);
       // S(j) is in registers: the tensor core may overwrite it with S(j+1)
       tc_fence_before();
       __syncwarp();
@@ -291,8 +303,8 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (32 + k >= tail_valid) s1[k] = 0xFF800000u;
       }
       const float hmax = fmaxf(cols_max<32>(s0), cols_max<8>(s1));
-      publish(hmax, j);
-      if constexpr (kFirst) m_used = fmaxf(hmax, collect(j, false)) * p.scale_log2;
+      A8_TS(3);
+      if constexpr (kFirst) m_used = fmaxf(hmax, exchange(hmax, j)) * p.scale_log2;
       uint64_t acc[2] = {0ull, 0ull};
       uint32_t pk0[16], pk1[4];
       {
@@ -300,11 +312,14 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         exp_cols<kEmuPairs, 32>(s0, scale2, negm2, acc, pk0);
         exp_cols<kEmuPairs, 8>(s1, scale2, negm2, acc, pk1);
       }
+      A8_TS(4);
       if constexpr (!kFirst) {
         // true row max of this block (log2 domain); both threads of the row see the same value
-        const float m_cur = fmaxf(hmax, collect(j, false)) * p.scale_log2;
+        const float m_cur = fmaxf(hmax, exchange(hmax, j)) * p.scale_log2;
+        A8_TS(5);
         // PV(j-1, i) must have drained P (and, for a rescale, O) before either is written
         mbar_wait(p_free(i), (j - 1) & 1);
+        A8_TS(6);
         tc_fence_after();
         const bool need = m_cur > m_used + A8_RESCALE_THRESHOLD;
         if (__any_sync(0xffffffffu, need)) {
@@ -334,6 +349,7 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(i));
+      A8_TS(7);
       float a0, a1, a2, a3;
       unpack2(acc[0], a0, a1);
       unpack2(acc[1], a2, a3);
@@ -344,8 +360,7 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int j = 1; j < n_kv; ++j) kv_block(j, std::false_type{});
 
     // ---------------- epilogue: O / l -> bf16 -> global (this thread: 64 of the row's 128 columns)
-    publish(l, n_kv);
-    const float inv_l = 1.0f / (l + collect(n_kv, true));
+    const float inv_l = 1.0f / (l + exchange(l, n_kv));
     mbar_wait(p_free(i), (n_kv - 1) & 1);
     tc_fence_after();
     __nv_bfloat16* orow;
@@ -382,10 +397,10 @@ gf_attn80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
-template <int kEmuPairs, int kXchg>
+template <int kEmuPairs>
 static int launch80(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const Attn80Params& p,
                     cudaStream_t stream) {
-  auto kern = gf_attn80_kernel<kEmuPairs, kXchg>;
+  auto kern = gf_attn80_kernel<kEmuPairs>;
   static bool configured[64] = {};
   if (int rc = gf_set_smem_once(configured, reinterpret_cast<const void*>(kern), A8_SMEM_BYTES)) return rc;
   const int items = p.q_blocks * p.heads;
@@ -394,7 +409,7 @@ static int launch80(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtens
 }
 
 int gf_attention80_launch(gf_ctx* ctx, const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
-                          const AttnOut& out, int Lq, int Lk, int heads, float scale, int emu_pairs, int xchg,
+                          const AttnOut& out, int Lq, int Lk, int heads, float scale, int emu_pairs,
                           cudaStream_t stream) {
   CUtensorMap scr[3];
   int rc = 0;
@@ -405,6 +420,11 @@ int gf_attention80_launch(gf_ctx* ctx, const void* Q, long long ldq, const void*
   const CUtensorMap* tmV = gf_ctx_tmap(ctx, &scr[2], V, (uint64_t)heads * A8_D, (uint64_t)Lk, (uint64_t)ldv, 64, A8_BN, &rc);
   if (!tmV) return rc;
   Attn80Params p;
+#ifdef GF_A8_TRACE
+  p.trace = g_a8_trace;
+#else
+  p.trace = nullptr;
+#endif
   p.out = out;
   p.Lq = Lq; p.Lk = Lk; p.heads = heads;
   p.q_blocks = (Lq + 2 * A8_BM - 1) / (2 * A8_BM);
@@ -413,20 +433,19 @@ int gf_attention80_launch(gf_ctx* ctx, const void* Q, long long ldq, const void*
   const int tail = sms > 0 ? items % sms : 0;
   p.n_full = (tail > 0 && items > sms && 2 * tail <= sms) ? items - tail : items;
   p.scale_log2 = scale * 1.4426950408889634f;
-  auto go = [&](auto xtag) -> int {
-    constexpr int kX = decltype(xtag)::value;
-    switch (emu_pairs) {
-      case 0: return launch80<0, kX>(*tmQ, *tmK, *tmV, p, stream);
-      case 2: return launch80<2, kX>(*tmQ, *tmK, *tmV, p, stream);
-      case 6: return launch80<6, kX>(*tmQ, *tmK, *tmV, p, stream);
-      default: return launch80<4, kX>(*tmQ, *tmK, *tmV, p, stream);
-    }
-  };
-  switch (xchg) {
-    case 0: return go(std::integral_constant<int, 0>{});
-    case 1: return go(std::integral_constant<int, 1>{});
-    default: return go(std::integral_constant<int, 2>{});
+  switch (emu_pairs) {
+    case 0: return launch80<0>(*tmQ, *tmK, *tmV, p, stream);
+    case 2: return launch80<2>(*tmQ, *tmK, *tmV, p, stream);
+    case 6: return launch80<6>(*tmQ, *tmK, *tmV, p, stream);
+    default: return launch80<4>(*tmQ, *tmK, *tmV, p, stream);
   }
 }
 
 }  // namespace gf
+
+#ifdef GF_A8_TRACE
+extern "C" int gf_debug_attn_trace(void* buf) {
+  gf::g_a8_trace = reinterpret_cast<long long*>(buf);
+  return 0;
+}
+#endif

@@ -87,6 +87,17 @@ __device__ __forceinline__ float cols_max(const uint32_t (&s)[kCols]) {
   for (int k = 1; k < kCols / 2; ++k) m = fmax3(m, __uint_as_float(s[2 * k]), __uint_as_float(s[2 * k + 1]));
   return m;
 }
+// same maximum through four independent chains (depth kCols/8 + 2 instead of kCols/2)
+template <int kCols>
+__device__ __forceinline__ float cols_max4(const uint32_t (&s)[kCols]) {
+  static_assert(kCols % 8 == 0, "cols_max4 needs a multiple of 8 columns");
+  float m[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) m[c] = fmaxf(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1]));
+#pragma unroll
+  for (int k = 4; k < kCols / 2; ++k) m[k & 3] = fmax3(m[k & 3], __uint_as_float(s[2 * k]), __uint_as_float(s[2 * k + 1]));
+  return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+}
 __device__ __forceinline__ float chunk_max(const uint32_t (&s)[32]) { return cols_max<32>(s); }
 
 }  // namespace gf

@@ -57,38 +57,56 @@ def image_condition(vae_latents: torch.Tensor, num_frames: int, end_image: bool 
 
 @dataclass
 class ParallelLayout:
-    """rank = cfg_index * sp_size + sp_index.  cfg_size in {1, 2}; sp_size must divide the head count and tokens."""
+    """rank = replica * (cfg_size * sp_size) + cfg_index * sp_size + sp_index.
+    cfg_size in {1, 2}; sp_size must divide the head count and the token count; `replicas` independent copies of the
+    (cfg x sp) grid work on different jobs (the reference's only multi-GPU mode: one process per CSV shard,
+    scripts/inference/utils.py:25-57)."""
     world_size: int = 1
     rank: int = 0
     cfg_size: int = 1
+    replicas: int = 1
 
     def __post_init__(self):
-        if self.cfg_size not in (1, 2) or self.world_size % self.cfg_size:
-            raise ValueError(f"cfg_size {self.cfg_size} does not fit world size {self.world_size}")
+        if self.cfg_size not in (1, 2) or self.replicas < 1 or self.world_size % (self.cfg_size * self.replicas):
+            raise ValueError(f"cfg_size {self.cfg_size} x replicas {self.replicas} does not fit world size "
+                             f"{self.world_size}")
+
+    @property
+    def group_size(self) -> int:
+        """ranks that cooperate on one job"""
+        return self.world_size // self.replicas
 
     @property
     def sp_size(self) -> int:
-        return self.world_size // self.cfg_size
+        return self.group_size // self.cfg_size
+
+    @property
+    def replica(self) -> int:
+        return self.rank // self.group_size
 
     @property
     def cfg_index(self) -> int:
-        return self.rank // self.sp_size
+        return (self.rank % self.group_size) // self.sp_size
 
     @property
     def sp_index(self) -> int:
         return self.rank % self.sp_size
 
-    def sp_ranks(self, cfg_index: int | None = None):
+    def sp_ranks(self, cfg_index: int | None = None, replica: int | None = None):
         c = self.cfg_index if cfg_index is None else cfg_index
-        return [c * self.sp_size + i for i in range(self.sp_size)]
+        r = self.replica if replica is None else replica
+        base = r * self.group_size + c * self.sp_size
+        return [base + i for i in range(self.sp_size)]
 
-    def cfg_ranks(self, sp_index: int | None = None):
+    def cfg_ranks(self, sp_index: int | None = None, replica: int | None = None):
         s = self.sp_index if sp_index is None else sp_index
-        return [c * self.sp_size + s for c in range(self.cfg_size)]
+        r = self.replica if replica is None else replica
+        return [r * self.group_size + c * self.sp_size + s for c in range(self.cfg_size)]
 
 
 class ParallelContext:
-    """torch.distributed groups for a ParallelLayout (every rank must construct it: new_group is collective)."""
+    """torch.distributed groups for a ParallelLayout (every rank must construct it: new_group is collective and
+    every rank creates every group, in the same order)."""
 
     def __init__(self, layout: ParallelLayout, transport: str = "peer"):
         import torch.distributed as dist
@@ -97,14 +115,15 @@ class ParallelContext:
         self.sp_group = None
         self.cfg_group = None
         if layout.world_size > 1:
-            for c in range(layout.cfg_size):
-                g = dist.new_group(layout.sp_ranks(c))
-                if c == layout.cfg_index:
-                    self.sp_group = g
-            for s in range(layout.sp_size):
-                g = dist.new_group(layout.cfg_ranks(s))
-                if s == layout.sp_index:
-                    self.cfg_group = g
+            for r in range(layout.replicas):
+                for c in range(layout.cfg_size):
+                    g = dist.new_group(layout.sp_ranks(c, r)) if layout.sp_size > 1 else None
+                    if r == layout.replica and c == layout.cfg_index:
+                        self.sp_group = g
+                for s in range(layout.sp_size):
+                    g = dist.new_group(layout.cfg_ranks(s, r)) if layout.cfg_size > 1 else None
+                    if r == layout.replica and s == layout.sp_index:
+                        self.cfg_group = g
         self.sp = SequenceParallel(self.sp_group, transport=transport) if layout.sp_size > 1 else None
 
 

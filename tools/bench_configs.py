@@ -10,6 +10,11 @@
            switch at t < 875, goal-force ControlNet (10 blocks) on the high-noise expert, never-loaded (all-zero,
            skipped) ControlNet on the low-noise expert as in the shipped inference script; 81x480x832.
   long   : configs[4] -- attention-bound stress, one forward of the high-noise expert + ControlNet at 720x1280.
+  direct : configs[3] -- Direct Force mode (projectile force + mass channels), a batch of 4 CSV rows through
+           goal_force_b200.jobs.BatchDriver: control videos synthesised bit-exactly on the host (overlapped with the
+           previous row's denoising), encoded by a synthetic stand-in for the VAE, then the full two-expert sampling.
+           Layout: --replicas R --cfg-parallel, e.g. 8 GPUs as cfg 2 x ulysses 4 (R = 1, rows one after the other)
+           or as 4 replicas x cfg 2 (R = 4, one row per replica).  Reports videos/s and denoise steps/s.
 Random-init weights, synthetic latents. Prints one JSON line on rank 0. Timing: CUDA events, max over ranks.
 """
 from __future__ import annotations
@@ -26,7 +31,9 @@ sys.path.insert(0, str(ROOT))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=["sample", "long"])
+    ap.add_argument("--config", required=True, choices=["sample", "long", "direct"])
+    ap.add_argument("--replicas", type=int, default=1)
+    ap.add_argument("--rows", type=int, default=4)
     ap.add_argument("--steps", type=int, default=40, help="sample: denoise steps; long: timed forwards")
     ap.add_argument("--frames", type=int, default=81)
     ap.add_argument("--cfg-parallel", action="store_true")
@@ -46,8 +53,8 @@ def main():
     from goal_force_b200.wan_dit import ControlNetB200, WAN22_I2V_A14B as cfg, WanModelB200, model_fn_wan_video
     capi.load()
     cfg_size = 2 if (args.cfg_parallel and world > 1) else 1
-    par = (ParallelContext(ParallelLayout(world_size=world, rank=rank, cfg_size=cfg_size), transport=args.transport)
-           if world > 1 else None)
+    par = (ParallelContext(ParallelLayout(world_size=world, rank=rank, cfg_size=cfg_size, replicas=args.replicas),
+                           transport=args.transport) if world > 1 else None)
 
     def sync():
         if world > 1:
@@ -93,6 +100,37 @@ def main():
             + 10 * 2.0 * L * d * d
         line = {"config": f"configs[4]: A14B DiT forward + 10-block ControlNet at {args.frames}x720x1280", "tokens": L,
                 "ms_per_forward": ms, "forwards_per_s": 1000.0 / ms, "tflops_per_gpu": flops / 1e12 / (ms / 1e3) / world}
+    elif args.config == "direct":
+        from goal_force_b200 import jobs as J
+        golden = json.loads((ROOT / "tests" / "golden" / "control_channels.json").read_text())
+        names = ["_pendulum", "_toycar", "_cantaloupes", "_paw_tool2", "_golf", "_tennis", "_soccer_tool", "_pool_tool"]
+        rows = [J.direct_force_row(golden["rows"][names[i % len(names)]], 250.0, 37.0, 2.5) for i in range(args.rows)]
+        dit2 = WanModelB200(cfg, lazy(2), device=dev)
+        cn2 = ControlNetB200(cfg, lazy(3, controlnet_layers=10, zero_convs=True), 10, device=dev)
+        inp = synthetic_inputs(cfg, 21, 60, 104, seed=1, device=dev)
+        ctx_n = torch.randn(1, 512, cfg.text_dim, generator=torch.Generator("cpu").manual_seed(7)).to(dev, torch.bfloat16)
+        den = GoalForceDenoiser(dit, dit2, cn, cn2, parallel=par)
+        cond = lambda row: dict(context_posi=inp["context"], context_nega=ctx_n, y=inp["y"])  # noqa: E731
+        mk = lambda steps: J.BatchDriver(den, J.synthetic_control_encoder(dev), cond, parallel=par,  # noqa: E731
+                                         num_inference_steps=steps, device=dev)
+        mk(2).run(rows[:max(1, args.replicas)])                     # warm-up: both experts, caches, exchange buffers
+        sync()
+        e0.record()
+        out = mk(args.steps).run(rows, seed=0)
+        e1.record()
+        sync()
+        ms = elapsed_max_ms()
+        assert all(not torch.isnan(j.result).any() for j in out)
+        import hashlib
+
+        def digest(t):       # the SHA-256 prefix recorded in tests/golden/control_channels.json
+            return hashlib.sha256(t.contiguous().view(torch.int16).numpy().tobytes()).hexdigest()[:16]
+        ok = all(digest(j.control_video) == golden["direct_force"][names[j.index % len(names)]]
+                 for j in out if names[j.index % len(names)] in golden["direct_force"])
+        line = {"config": f"configs[3]: Direct Force, {args.rows} CSV rows, {args.steps} steps each, CFG 5.0, 81x480x832",
+                "tokens": 32760, "seconds_total": ms / 1e3, "videos_per_s": args.rows / (ms / 1e3),
+                "denoise_steps_per_s": args.rows * args.steps / (ms / 1e3), "rows_on_rank0": [j.index for j in out],
+                "control_videos_bit_exact_vs_reference_digests": ok}
     else:
         dit2 = WanModelB200(cfg, lazy(2), device=dev)
         cn2 = ControlNetB200(cfg, lazy(3, controlnet_layers=10, zero_convs=True), 10, device=dev)   # F6: exact no-op
@@ -116,7 +154,8 @@ def main():
         line = {"config": f"configs[2]: two-expert A14B sampling, {args.steps} steps, CFG 5.0, 81x480x832", "tokens": 32760,
                 "seconds_per_video_denoise": ms / 1e3, "denoise_steps_per_s": args.steps / (ms / 1e3),
                 "high_noise_steps": used.count(0), "low_noise_steps": used.count(1)}
-    line.update(n_gpus=world, layout=f"cfg{cfg_size} x ulysses{world // cfg_size}" + (f" ({args.transport})" if world > 1 else ""),
+    line.update(n_gpus=world, layout=f"{args.replicas} replica(s) x cfg{cfg_size} x ulysses{world // cfg_size // args.replicas}"
+                + (f" ({args.transport})" if world > 1 else ""),
                 dtype="bf16", data="synthetic, random-init weights")
     if rank == 0:
         print(json.dumps(line), flush=True)
