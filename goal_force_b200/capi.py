@@ -156,9 +156,37 @@ class LaunchStats:
 
 STATS = LaunchStats()
 
+# NVTX ranges (tracing): GF_B200_NVTX=1 (read once at import) or capi.NVTX = True wraps every launch in a
+# range named after its kernel class and lets the host code mark forward / block / branch ranges with nvtx_range().
+NVTX = os.environ.get("GF_B200_NVTX", "0") == "1"
+
+
+class nvtx_range:
+    """`with capi.nvtx_range("trunk.block3"):` -- a no-op unless capi.NVTX is set."""
+
+    def __init__(self, name: str):
+        self.name, self.on = name, NVTX
+
+    def __enter__(self):
+        if self.on:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
 
 def _call(tag: str, work: float, fn, *args) -> None:
     STATS.launches += 1
+    if NVTX:
+        torch.cuda.nvtx.range_push("gf." + tag)
+        try:
+            _check(fn(*args), tag)
+        finally:
+            torch.cuda.nvtx.range_pop()
+        return
     if STATS.timing:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

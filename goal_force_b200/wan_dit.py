@@ -425,13 +425,13 @@ class WanModelB200:
             self._rope_cache = {key: t}
         return t
 
-    def context_entry(self, context: torch.Tensor) -> tuple:
+    def context_entry(self, context: torch.Tensor, cache: bool = True) -> tuple:
         """text_embedding (wan_video_dit.py:309-313,371) + per-block cross-attention K/V, cached per context tensor
         (the pipeline passes the same prompt embedding at every step).  Returns the cache entry
         (context, [K|V per block], embedding); the entry keeps `context` alive, so its address cannot be recycled
         while the entry is cached.  Tensors without a version counter (torch.inference_mode) are not cached."""
         try:
-            key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype)
+            key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype) if cache else None
         except RuntimeError:
             key = None
         hit = self._ctx_cache.get(key) if key is not None else None
@@ -556,10 +556,13 @@ class ControlNetB200:
                         num_layers=module.num_layers)
         return cls(cfg, module.state_dict(), module.num_layers, stride=module.stride, device=device)
 
-    def control_tokens(self, control_latents: torch.Tensor) -> torch.Tensor:
+    def control_tokens(self, control_latents: torch.Tensor, cache: bool = True) -> torch.Tensor:
         """ControlNet_PatchEmbedding (wan_video_new.py:72-94); step-invariant, cached per latent tensor."""
-        key = (control_latents.data_ptr(), control_latents._version, tuple(control_latents.shape))
-        hit = self._patch_cache.get(key)    # entry keeps the latent tensor alive
+        try:
+            key = (control_latents.data_ptr(), control_latents._version, tuple(control_latents.shape)) if cache else None
+        except RuntimeError:
+            key = None
+        hit = self._patch_cache.get(key) if key is not None else None   # entry keeps the latent tensor alive
         if hit is not None:
             return hit[1]
         c = control_latents
@@ -569,18 +572,21 @@ class ControlNetB200:
             c = c[0]
         c = c.to(device=self.device, dtype=torch.bfloat16).contiguous()
         tok = capi.gemm(capi.patch_gather(c, None), self.patch_w, self.patch_b)
-        self._patch_cache = {key: (control_latents, tok)}
+        if key is not None:
+            self._patch_cache = {key: (control_latents, tok)}
         return tok
 
-    def context_kv(self, entry: tuple) -> list:
+    def context_kv(self, entry: tuple, cache: bool = True) -> list:
         """Cross-attention K|V of the ControlNet blocks for one prompt.  `entry` is the trunk's cache entry
         (WanModelB200.context_entry): the ControlNet result is keyed by that object's identity and keeps it -- and
         with it the context tensor -- alive, so a recycled address or a trunk-side eviction can never alias a stale
         ControlNet entry."""
-        hit = self._ctx_cache.get(id(entry))
+        hit = self._ctx_cache.get(id(entry)) if cache else None
         if hit is not None and hit[0] is entry:
             return hit[1]
         kvs = [block_context_kv(b, self.cfg, entry[2]) for b in self.blocks]
+        if not cache:
+            return kvs
         if len(self._ctx_cache) >= 4:
             self._ctx_cache.clear()
         self._ctx_cache[id(entry)] = (entry, kvs)
@@ -653,7 +659,8 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
                        sliding_window_size=None, sliding_window_stride=None, cfg_merge=False,
                        use_gradient_checkpointing=False, use_gradient_checkpointing_offload=False,
                        control_camera_latents_input=None, fuse_vae_embedding_in_latents=False, controlnet=None,
-                       sequence_parallel: SequenceParallel | None = None, **kwargs):
+                       sequence_parallel: SequenceParallel | None = None, _recompute_step_invariants: bool = False,
+                       **kwargs):
     """Drop-in for pipe.model_fn (src/goal_force/wan_video_new.py:1349-1591), goal-force configuration.
 
     Same keyword surface as the reference; extra keywords are accepted and ignored (the pipeline passes its whole
@@ -692,7 +699,8 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
         if y is not None and dit.require_vae_embedding:
             yb = y[min(b, y.shape[0] - 1)].to(device=dit.device, dtype=torch.bfloat16).contiguous()
         ctx_b = context[b:b + 1] if context.shape[0] > 1 else context
-        ctx_entry = dit.context_entry(ctx_b)
+        use_cache = not _recompute_step_invariants      # graph capture: every tensor input is a static buffer
+        ctx_entry = dit.context_entry(ctx_b, cache=use_cache)
         ctx_kv = ctx_entry[1]
         x, (f, h, w) = dit.patchify(lat, yb)                                                    # :1464
         L = f * h * w
@@ -707,21 +715,23 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
             csl = kwargs.get("control_signal_video_latents", None)
             if csl is None:
                 raise ValueError("controlnet given but control_signal_video_latents is missing")
-            s = controlnet.control_tokens(csl)
+            s = controlnet.control_tokens(csl, cache=use_cache)
             if s.shape[0] != L:
                 raise ValueError("control latents and latents have different token counts")
             if sp is not None:
                 s = s[sp.token_slice(L)]
-            cn_kv = controlnet.context_kv(ctx_entry)
+            cn_kv = controlnet.context_kv(ctx_entry, cache=use_cache)
             # ControlNet blocks share t_mod with the trunk but carry their own modulation tables
             cn_tab = capi.add_rows(controlnet.block_mod, t_mod_flat).view(controlnet.num_layers, 6, cfg.dim)
             states = ws.cn_states(controlnet.num_layers)       # block i: state i-1 (or the patch tokens) -> state i
             for i, bw in enumerate(controlnet.blocks):
-                run_block(bw, cfg, states[i], cn_kv[i], cn_tab[i], cos_sin, ws, sp, x_in=s)
+                with capi.nvtx_range(f"controlnet.block{i}"):
+                    run_block(bw, cfg, states[i], cn_kv[i], cn_tab[i], cos_sin, ws, sp, x_in=s)
                 s = states[i]
 
         for i, bw in enumerate(dit.blocks):                                                     # :1540-1570
-            run_block(bw, cfg, x, ctx_kv[i], block_tab[i], cos_sin, ws, sp)
+            with capi.nvtx_range(f"trunk.block{i}"):
+                run_block(bw, cfg, x, ctx_kv[i], block_tab[i], cos_sin, ws, sp)
             if use_cn:
                 if controlnet.stride is not None:
                     if i % controlnet.stride == 0 and i // controlnet.stride < len(states):

@@ -247,3 +247,30 @@ def test_models_from_safetensors_equal_models_from_state_dict(tmp_path):
     kw = dict(latents=inp["latents"], timestep=inp["timestep"], context=inp["context"], y=inp["y"],
               control_signal_video_latents=inp["control_signal_video_latents"])
     assert torch.equal(model_fn_wan_video(dit=dit_a, controlnet=cn_a, **kw), model_fn_wan_video(dit=dit_b, controlnet=cn_b, **kw))
+
+
+def test_cuda_graph_replay_equals_eager():
+    """GraphedModelFn: one capture per (expert, shapes), every tensor input static, step-invariants recomputed inside
+    the graph; replays with new latents / timestep / prompt / control latents equal the eager forward bit for bit, and
+    the descriptor cache of the context is hit on every launch after the first forward."""
+    from goal_force_b200 import capi
+    from goal_force_b200.graph import GraphedModelFn
+    from goal_force_b200.wan_dit import ControlNetB200, WanModelB200, model_fn_wan_video
+    cfg = O.DiTConfig(dim=1536, in_dim=36, ffn_dim=4096, out_dim=16, text_dim=256, freq_dim=256, eps=1e-6,
+                      num_heads=12, num_layers=2)
+    pc = _prod_cfg(cfg)
+    dit = WanModelB200(pc, O.random_state_dict(cfg, seed=50))
+    cn = ControlNetB200(pc, O.random_controlnet_state_dict(cfg, 1, seed=51), 1)
+    gfn = GraphedModelFn()
+    before = capi.ctx_stats()
+    for k in range(3):
+        inp = O.synthetic_inputs(cfg, 3, 16, 24, seed=60 + k, ctx_len=64, ctx_valid=16, timestep=990.0 - 100 * k)
+        bf = {n: v.to("cuda", torch.bfloat16) for n, v in inp.items()}
+        kw = dict(dit=dit, controlnet=cn, latents=bf["latents"], timestep=bf["timestep"], context=bf["context"],
+                  y=bf["y"], control_signal_video_latents=bf["control_signal_video_latents"])
+        want = model_fn_wan_video(**kw)
+        got = gfn(**kw)
+        assert torch.equal(got, want), k
+    assert gfn.captures == 1 and gfn.replays == 3
+    after = capi.ctx_stats()
+    assert after["tmap_hits"] > before["tmap_hits"] and after["tmap_entries"] > 0

@@ -19,7 +19,7 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, mode, transport, ret):
+def _worker(rank, world, port, mode, transport, ret, shape=(4, 40, 52)):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -33,7 +33,7 @@ def _worker(rank, world, port, mode, transport, ret):
         cfg = DiTConfig(**ocfg.__dict__)
         sd = O.random_state_dict(ocfg, seed=2)
         csd = O.random_controlnet_state_dict(ocfg, 1, seed=3)
-        inp = {k: v.to(dev, torch.bfloat16) for k, v in O.synthetic_inputs(ocfg, 4, 40, 52, seed=4, timestep=990.0).items()}
+        inp = {k: v.to(dev, torch.bfloat16) for k, v in O.synthetic_inputs(ocfg, *shape, seed=4, timestep=990.0).items()}
         dit = WanModelB200(cfg, sd, device=dev)
         cn = ControlNetB200(cfg, csd, 1, device=dev)
         kw = dict(dit=dit, controlnet=cn, latents=inp["latents"], timestep=inp["timestep"], context=inp["context"],
@@ -70,12 +70,12 @@ def _worker(rank, world, port, mode, transport, ret):
         dist.destroy_process_group()
 
 
-def _run(mode, transport="peer", world=2):
+def _run(mode, transport="peer", world=2, shape=(4, 40, 52)):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), mode, transport, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), mode, transport, ret, shape), nprocs=world, join=True)
     assert ret.get("ok"), f"{mode} x{world}: multi-GPU result differs from single-GPU (max abs diff {ret.get('err')})"
     print(f"{mode} world {world} transport {transport}: bit-identical to the single-GPU result")
 
@@ -94,3 +94,10 @@ def test_cfg_parallel_bit_identical_to_sequential(lib, world):
     """cfg 2 (world 2), cfg 2 x sp 2 (world 4), cfg 2 x sp 4 (world 8, BASELINE configs[3] layout) against
     sequential CFG on one GPU."""
     _run("cfg", "peer", world)
+
+
+@pytest.mark.timeout(900)
+def test_ulysses_sp8_long_sequence_bit_identical(lib):
+    """BASELINE configs[4]: 81 x 720 x 1280 = 75,600 tokens over 8 GPUs (9,450 tokens and 5 heads per rank), fused
+    peer exchange, against the same forward on one GPU."""
+    _run("sp", "peer", 8, shape=(21, 90, 160))

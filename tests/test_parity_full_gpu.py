@@ -190,6 +190,40 @@ def test_strided_controlnet_vs_oracle():
     assert _bound(e_ours, e_ref), (e_ours, e_ref)
 
 
+def test_long_sequence_75600_tokens_vs_oracle():
+    """BASELINE configs[4] length: 81 x 720 x 1280 -> latent 21 x 90 x 160 -> 75,600 tokens (590 two-tile work items per
+    head: the attention tail splitting and the 2.3x longer kv loop are exercised), A14B widths, 2 trunk + 1 ControlNet
+    block, against the oracle on this device."""
+    from goal_force_b200.wan_dit import ControlNetB200, WanModelB200, model_fn_wan_video
+    cfg = O.DiTConfig(**{**O.WAN22_I2V_A14B.__dict__, "num_layers": 2})
+    sd = O.random_state_dict(cfg, seed=70)
+    csd = O.random_controlnet_state_dict(cfg, 1, seed=71)
+    inp = O.synthetic_inputs(cfg, 21, 90, 160, seed=72, timestep=937.0)
+    outs = []
+    for dt in (torch.float32, torch.bfloat16):
+        s_ = {k: v.to("cuda", dt) for k, v in sd.items()}
+        c_ = {k: v.to("cuda", dt) for k, v in csd.items()}
+        i = {k: v.to("cuda", dt) for k, v in inp.items()}
+        with torch.no_grad():
+            outs.append(O.model_fn(s_, cfg, i["latents"], i["timestep"], i["context"], y=i["y"], controlnet_sd=c_,
+                                   control_signal_video_latents=i["control_signal_video_latents"],
+                                   controlnet_num_layers=1).cpu())
+        del s_, c_, i
+        _free()
+    ref32, refbf = outs
+    pc = _prod_cfg(cfg)
+    bf = {k: v.to("cuda", torch.bfloat16) for k, v in inp.items()}
+    out = model_fn_wan_video(dit=WanModelB200(pc, sd), controlnet=ControlNetB200(pc, csd, 1), latents=bf["latents"],
+                             timestep=bf["timestep"], context=bf["context"], y=bf["y"],
+                             control_signal_video_latents=bf["control_signal_video_latents"]).cpu()
+    assert out.shape == (1, 16, 21, 90, 160)
+    e_ours, e_ref = O.rel_l2(out, ref32), O.rel_l2(refbf, ref32)
+    print(f"75,600 tokens (81x720x1280), 2+1 blocks: relL2 ours-vs-fp32 {e_ours:.3e} ref_bf16-vs-fp32 {e_ref:.3e} "
+          f"ours-vs-ref_bf16 {O.rel_l2(out, refbf):.3e}")
+    _free()
+    assert _bound(e_ours, e_ref), (e_ours, e_ref)
+
+
 def test_reference_modules_through_model_fn():
     """INTEGRATION.md recipe: `pipe.model_fn = model_fn_wan_video` with the pipeline's own nn.Modules (stand-ins with the
     reference's attribute tree and state_dict keys, oracle/ref_standins.py) living on the GPU in bf16.  They are
