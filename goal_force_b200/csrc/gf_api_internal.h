@@ -26,7 +26,8 @@ const CUtensorMap* gf_ctx_tmap(gf_ctx* ctx, CUtensorMap* scratch, const void* ba
 
 // Per-context tuning (0 / negative = library default).
 struct CtxTuning {
-  int attn_impl = 0;       // 0: per shape (80 for long key sequences, 128 for Lk <= 1024); 80 / 128: forced
+  int attn_impl = 0;       // 0: per shape (80 / 160 for long key sequences, 128 for Lk <= 1024); 80 / 128 / 160: forced
+                           // (160 = CTA-pair variant of 80)
   int attn_emu = -1;       // -1: kernel default; 0, 2, 4, 6: column pairs per 16 with exp2 on the FMA pipe
   int gemm_group_m = 0;    // 0: per shape; > 0: rasterisation group height in m-tiles
 };
@@ -58,5 +59,10 @@ struct AttnOut {
 int gf_attention80_launch(gf_ctx* ctx, const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
                           const AttnOut& out, int Lq, int Lk, int heads, float scale, int emu_pairs,
                           cudaStream_t stream);
+
+// gf_attn80x2.cu: CTA-pair (cta_group::2) variant of the same kernel; work items of 512 query rows.
+int gf_attention80x2_launch(gf_ctx* ctx, const void* Q, long long ldq, const void* K, long long ldk, const void* V,
+                            long long ldv, const AttnOut& out, int Lq, int Lk, int heads, float scale, int emu_pairs,
+                            cudaStream_t stream);
 
 }  // namespace gf

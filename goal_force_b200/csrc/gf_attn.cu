@@ -325,11 +325,20 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 //               -1 = kernel default (0 for impl 80, 4 for impl 128)
 // Short key sequences (cross-attention against 512 context tokens) are a handful of kv blocks per CTA: there the
 // 128-row-block kernel wastes fewer padded columns (512 = 4 x 128 vs 7 x 80) and measures ~8 % faster.
-static int attn_impl_for(const CtxTuning& t, int Lk) {
-  if (t.attn_impl == 80 || t.attn_impl == 128) return t.attn_impl;
-  return Lk <= 1024 ? 128 : 80;
+// Long key sequences take the 80-row-block kernel; its CTA-pair form (160, gf_attn80x2.cu: QK no longer bound by the
+// shared-memory reads of the tensor core, +5 % measured) whenever the 512-row work items fill the 74 SM pairs well --
+// it has no tail splitting, so a launch whose last wave would be mostly empty (e.g. 5 heads x 64 items = 4.3 waves on
+// 8 GPUs) stays on the single-CTA kernel.
+static int attn_impl_for(const CtxTuning& t, int Lq, int Lk, int heads) {
+  if (t.attn_impl == 80 || t.attn_impl == 128 || t.attn_impl == 160) return t.attn_impl;
+  if (Lk <= 1024) return 128;
+  const long long items = (long long)((Lq + 511) / 512) * heads;
+  const long long pairs = gf_num_sms() / 2;
+  if (pairs <= 0) return 80;
+  const long long waves = (items + pairs - 1) / pairs;
+  return (items * 100 >= waves * pairs * 95) ? 160 : 80;
 }
-static int attn_emu_for(const CtxTuning& t, int impl) { return t.attn_emu >= 0 ? t.attn_emu : (impl == 80 ? 0 : 4); }
+static int attn_emu_for(const CtxTuning& t, int impl) { return t.attn_emu >= 0 ? t.attn_emu : (impl == 128 ? 4 : 0); }
 
 template <int kEmuPairs>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p,
@@ -355,9 +364,10 @@ static int attention_dispatch(gf_ctx* ctx, const void* Q, long long ldq, const v
     if (!out.base[i] || (reinterpret_cast<uintptr_t>(out.base[i]) & 15)) return GF_ERR_BAD_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const CtxTuning tune = gf_ctx_tuning(ctx);
-  const int impl = attn_impl_for(tune, Lk);
+  const int impl = attn_impl_for(tune, Lq, Lk, heads);
   const int emu = attn_emu_for(tune, impl);
   if (impl == 80) return gf_attention80_launch(ctx, Q, ldq, K, ldk, V, ldv, out, Lq, Lk, heads, scale, emu, s);
+  if (impl == 160) return gf_attention80x2_launch(ctx, Q, ldq, K, ldk, V, ldv, out, Lq, Lk, heads, scale, emu, s);
   CUtensorMap scr[3];
   int rc = 0;
   const CUtensorMap* tmQ = gf_ctx_tmap(ctx, &scr[0], Q, (uint64_t)heads * AT_D, (uint64_t)Lq, (uint64_t)ldq, 64, AT_BM, &rc);

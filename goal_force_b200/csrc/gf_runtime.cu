@@ -119,7 +119,7 @@ extern "C" int gf_ctx_destroy(gf_ctx* ctx) {
 
 extern "C" int gf_ctx_set_attention(gf_ctx* ctx, int impl, int emu_pairs) {
   if (!ctx) return GF_ERR_BAD_ARG;
-  if ((impl != 0 && impl != 80 && impl != 128) ||
+  if ((impl != 0 && impl != 80 && impl != 128 && impl != 160) ||
       (emu_pairs != -1 && emu_pairs != 0 && emu_pairs != 2 && emu_pairs != 4 && emu_pairs != 6))
     return GF_ERR_BAD_ARG;
   ctx->tuning.attn_impl = impl;

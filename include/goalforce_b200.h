@@ -41,8 +41,9 @@ extern "C" {
 int gf_abi_version(void);
 
 /* Opaque per-caller context: TMA descriptor cache (keyed by address + geometry, so a descriptor is encoded once per
- * buffer instead of once per launch) and tuning.  gf_ctx_set_attention: impl 0 = per-shape choice (80-row decoupled
- * kernel for long key sequences, 128-row kernel for Lk <= 1024), 80 / 128 = forced; emu_pairs -1 = kernel default, or
+ * buffer instead of once per launch) and tuning.  gf_ctx_set_attention: impl 0 = per-shape choice (for long key
+ * sequences the 80-row decoupled kernel, as a CTA pair when the 512-row work items fill the SM pairs; the 128-row
+ * kernel for Lk <= 1024), 80 / 160 / 128 = forced (160 = CTA-pair form of 80); emu_pairs -1 = kernel default, or
  * 0/2/4/6 column pairs per 16 whose exp2 runs on the FMA pipe.  gf_ctx_set_gemm_raster: rasterisation group height in
  * m-tiles, 0 = per-shape choice.  gf_ctx_stats: descriptor-cache counters (any pointer may be NULL). */
 typedef struct gf_ctx gf_ctx;

@@ -124,7 +124,7 @@ def _attn_ref(q, k, v, heads):
     return F.scaled_dot_product_attention(qh, kh, vh)[0].transpose(0, 1).reshape(Lq, heads * 128)
 
 
-@pytest.fixture(params=[(80, 0), (80, 4), (128, 4), (128, 0)], ids=lambda p: f"impl{p[0]}-emu{p[1]}")
+@pytest.fixture(params=[(80, 0), (80, 4), (128, 4), (128, 0), (160, 0), (160, 4)], ids=lambda p: f"impl{p[0]}-emu{p[1]}")
 def attn_variant(capi, request):
     """every attention kernel variant selectable through gf_ctx_set_attention; the default is restored afterwards"""
     capi.attention_tuning(*request.param)
