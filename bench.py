@@ -34,12 +34,14 @@ CONTROLNET_LAYERS = 10
 
 
 def attn_dram_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE gf_attn80_kernel launch at this shape (L = 32760, 40 heads),
-    parsed from the newest committed `ncu --set full` summary profiles/rNN_attn80_ncu.csv (units are in the header).
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE self-attention launch (gf_attn80x2_kernel, the kernel the
+    library picks at this shape: L = 32760, 40 heads), parsed from the newest committed `ncu --set full` summary
+    profiles/rNN_attn80x2_ncu.csv (units are in the header; older rounds: rNN_attn80_ncu.csv).
     Returns (bytes, source) or (None, reason)."""
     import csv
     import re
-    cands = sorted((ROOT / "profiles").glob("r*_attn80_ncu.csv"), reverse=True)
+    cands = sorted((ROOT / "profiles").glob("r*_attn80x2_ncu.csv"), reverse=True) + \
+        sorted((ROOT / "profiles").glob("r*_attn80_ncu.csv"), reverse=True)
     for path in cands:
         try:
             rows = list(csv.reader(path.read_text().splitlines()))
@@ -315,7 +317,8 @@ def run_ours(args, emit):
     traffic, traffic_src = attn_dram_traffic()
     if att["launches"]:
         ach = att["work"] / att["ms"] / 1e9
-        roof = {"kernel": "gf_attn80_kernel (self-attention, tcgen05 flash attention)", "bound": "tensor",
+        roof = {"kernel": "gf_attn80x2_kernel (self-attention, tcgen05 flash attention, CTA pair)" if world == 1 else
+                          "self-attention (gf_attn80x2_kernel / gf_attn80_kernel by shape)", "bound": "tensor",
                 "achieved": round(ach, 1), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops"], 4),
                 "peak_source": f"{pk['source']} (cuBLAS bf16 sustained, MEASURED_PEAKS.json)",
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, parsed from the committed
