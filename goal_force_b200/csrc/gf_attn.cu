@@ -325,18 +325,15 @@ gf_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 //               -1 = kernel default (0 for impl 80, 4 for impl 128)
 // Short key sequences (cross-attention against 512 context tokens) are a handful of kv blocks per CTA: there the
 // 128-row-block kernel wastes fewer padded columns (512 = 4 x 128 vs 7 x 80) and measures ~8 % faster.
-// Long key sequences take the 80-row-block kernel; its CTA-pair form (160, gf_attn80x2.cu: QK no longer bound by the
-// shared-memory reads of the tensor core, +5 % measured) whenever the 512-row work items fill the 74 SM pairs well --
-// it has no tail splitting, so a launch whose last wave would be mostly empty (e.g. 5 heads x 64 items = 4.3 waves on
-// 8 GPUs) stays on the single-CTA kernel.
+// Long key sequences take the CTA-pair 80-row-block kernel (160, gf_attn80x2.cu: QK no longer bound by the
+// shared-memory reads of the tensor core; +5 % at 40 heads x 32,760 tokens, +3 % at 20 heads) once the launch is at
+// least 8 waves of 512-row items over the 74 SM pairs; with fewer waves (5 heads per GPU at 8 GPUs: 4.3 waves) the
+// coarser tail of the pair kernel eats the gain (measured 1264 vs 1254 TFLOP/s) and the single-CTA form (80) stays.
 static int attn_impl_for(const CtxTuning& t, int Lq, int Lk, int heads) {
   if (t.attn_impl == 80 || t.attn_impl == 128 || t.attn_impl == 160) return t.attn_impl;
   if (Lk <= 1024) return 128;
   const long long items = (long long)((Lq + 511) / 512) * heads;
-  const long long pairs = gf_num_sms() / 2;
-  if (pairs <= 0) return 80;
-  const long long waves = (items + pairs - 1) / pairs;
-  return (items * 100 >= waves * pairs * 95) ? 160 : 80;
+  return items >= 8LL * (gf_num_sms() / 2) ? 160 : 80;
 }
 static int attn_emu_for(const CtxTuning& t, int impl) { return t.attn_emu >= 0 ? t.attn_emu : (impl == 128 ? 4 : 0); }
 

@@ -39,6 +39,7 @@ struct Attn80x2Params {
   AttnOut out;
   int Lq, Lk, heads;
   int q_blocks;          // ceil(Lq / 512): work items per head (one per CTA pair)
+  int n_full;            // pairs [0, n_full) take a whole 512-row item; pairs beyond take one 256-row half of a tail item
   float scale_log2;
 };
 
@@ -64,10 +65,17 @@ gf_attn80x2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader_cta = cta_rank == 0;
-  const int item = (int)blockIdx.x >> 1;
+  // Work items are (head, 512 query rows) per CTA pair.  As in gf_attn80.cu, the items of a mostly empty last wave are
+  // split in two (`single`): such a pair takes 256 rows, one 128-row tile per CTA; tile 1's warps and issuer idle.
+  const int pair = (int)blockIdx.x >> 1;
+  const bool single = pair >= p.n_full;
+  const int tail_idx = single ? pair - p.n_full : 0;
+  const int item = single ? p.n_full + (tail_idx >> 1) : pair;
   const int head = item / p.q_blocks;
   const int qb = item % p.q_blocks;
-  const int q0 = qb * 4 * X2_BM + (int)cta_rank * 2 * X2_BM;     // first query row of this CTA
+  const int n_tiles = single ? 1 : 2;
+  const int q0 = qb * 4 * X2_BM + (single ? (tail_idx & 1) * 2 * X2_BM + (int)cta_rank * X2_BM
+                                          : (int)cta_rank * 2 * X2_BM);     // first query row of this CTA
   const int n_kv = (p.Lk + X2_BN - 1) / X2_BN;
   const int col0 = head * X2_D;
 
@@ -81,7 +89,7 @@ gf_attn80x2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(q_full, 1);
       for (int s = 0; s < X2_SLOTS; ++s) {
         mbar_init(kv_full(s), 1);
-        mbar_init(kv_empty(s), 2);   // both MMA issuers release a slot (multicast to both CTAs)
+        mbar_init(kv_empty(s), single ? 1 : 2);   // every active MMA issuer releases a slot (multicast to both CTAs)
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(s_full(i), 1);
@@ -113,8 +121,8 @@ gf_attn80x2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const bool lead = elect_one();
     const uint32_t q_full_l = mapa(q_full, 0);
     if (lead) {
-      if (leader_cta) mbar_arrive_expect_tx(q_full, 2 * 2 * X2_Q_BYTES);
-      for (int i = 0; i < 2; ++i)
+      if (leader_cta) mbar_arrive_expect_tx(q_full, 2 * n_tiles * X2_Q_BYTES);
+      for (int i = 0; i < n_tiles; ++i)
         for (int h = 0; h < 2; ++h)
           tma_load_2d_cg2(q_smem + i * X2_Q_BYTES + h * X2_QHALF, &tmQ, q_full_l, col0 + h * 64, q0 + i * X2_BM);
     }
@@ -148,7 +156,7 @@ gf_attn80x2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (j + 1 < n_kv) load_k(j + 1);
       load_v(j);
     }
-   } else if ((warp == 17 || warp == 18) && leader_cta) {
+   } else if ((warp == 17 || (warp == 18 && !single)) && leader_cta) {
     // ===================================================== MMA issuers (leader CTA): warp 17 tile 0, warp 18 tile 1
     const bool lead = elect_one();
     const int i = warp - 17;
@@ -205,7 +213,7 @@ gf_attn80x2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       advance();
     }
    }
-  } else {
+  } else if (!(single && warp >= 8)) {
     // ===================================================== softmax warpgroups (+ epilogue)
     setmaxnreg_inc<X2_SOFTMAX_REGS>();
     const int i = warp >> 3;                         // tile
@@ -355,7 +363,8 @@ static int launch80x2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
   static bool configured[64] = {};
   if (int rc = gf_set_smem_once(configured, reinterpret_cast<const void*>(kern), X2_SMEM_BYTES)) return rc;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * p.q_blocks * p.heads);
+  const int items = p.q_blocks * p.heads;
+  cfg.gridDim = dim3(2 * (p.n_full + 2 * (items - p.n_full)));
   cfg.blockDim = dim3(X2_THREADS);
   cfg.dynamicSmemBytes = X2_SMEM_BYTES;
   cfg.stream = stream;
@@ -384,6 +393,10 @@ int gf_attention80x2_launch(gf_ctx* ctx, const void* Q, long long ldq, const voi
   p.out = out;
   p.Lq = Lq; p.Lk = Lk; p.heads = heads;
   p.q_blocks = (Lq + 4 * X2_BM - 1) / (4 * X2_BM);
+  // tail splitting: if the items of the last partial wave fit on the SM pairs as half items, run them that way
+  const int items = p.q_blocks * heads, pairs = gf_num_sms() / 2;
+  const int tail = pairs > 0 ? items % pairs : 0;
+  p.n_full = (tail > 0 && items > pairs && 2 * tail <= pairs) ? items - tail : items;
   p.scale_log2 = scale * 1.4426950408889634f;
   switch (emu_pairs) {
     case 0: return launch80x2<0>(*tmQ, *tmK, *tmV, p, stream);
