@@ -45,6 +45,10 @@ SIGNATURES = {
     "gf_silu_bf16": [_p, _p, _ll, _p],
     "gf_cfg_euler_bf16": [_p, _p, _p, _p, _f, _f, _ll, _p],
     "gf_timestep_embedding_bf16": [_p, _p, _i, _i, _p],
+    "gf_embedding_bf16": [_p, _p, _p, _i, _i, _ll, _p],
+    "gf_t5_rmsnorm_bf16": [_p, _ll, _p, _ll, _i, _i, _p, _f, _p],
+    "gf_mul_bf16": [_p, _p, _p, _ll, _p],
+    "gf_t5_attention_bf16": [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p, _p, _p, _p],
     "gf_peer_alloc": [ctypes.POINTER(ctypes.c_void_p), _ll],
     "gf_peer_free": [_p],
     "gf_peer_export": [_p, _p],
@@ -422,6 +426,61 @@ def ulysses_unpack(inp: torch.Tensor, rows: int, heads: int, head_dim: int, P: i
         out = torch.empty((rows, heads * head_dim), dtype=torch.bfloat16, device=inp.device)
     _call("ulysses_pack", 4.0 * rows * heads * head_dim, load().gf_ulysses_unpack_bf16, inp.data_ptr(), out.data_ptr(),
           _ld(out), rows, heads, head_dim, P, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ umT5 encoder pieces
+def embedding(ids: torch.Tensor, table: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """ids: int64 [rows] on the device; table: [vocab, dim] bf16 -> [rows, dim]."""
+    _req(ids, "ids", torch.int64); _req(table, "table")
+    rows, dim = ids.numel(), table.shape[1]
+    if not ids.is_contiguous() or not table.is_contiguous():
+        raise ValueError("embedding needs contiguous ids and table")
+    if out is None:
+        out = torch.empty((rows, dim), dtype=torch.bfloat16, device=table.device)
+    _call("elementwise", 4.0 * rows * dim, load().gf_embedding_bf16, ids.data_ptr(), table.data_ptr(), out.data_ptr(),
+          rows, dim, table.shape[0], _stream())
+    return out
+
+
+def t5_rmsnorm(x: torch.Tensor, weight: torch.Tensor, *, eps: float, out: torch.Tensor | None = None) -> torch.Tensor:
+    _req(x, "x"); _req(weight, "weight")
+    rows, d = x.shape
+    if out is None:
+        out = torch.empty((rows, d), dtype=torch.bfloat16, device=x.device)
+    _call("rmsnorm_rope", 4.0 * rows * d, load().gf_t5_rmsnorm_bf16, x.data_ptr(), _ld(x), out.data_ptr(), _ld(out),
+          rows, d, weight.data_ptr(), eps, _stream())
+    return out
+
+
+def mul_(x: torch.Tensor, other: torch.Tensor) -> torch.Tensor:
+    """x *= other (same shape, contiguous), one bf16 rounding per element."""
+    _req(x, "x"); _req(other, "other")
+    if x.shape != other.shape or not x.is_contiguous() or not other.is_contiguous():
+        raise ValueError("mul_ needs two contiguous tensors of the same shape")
+    _call("elementwise", 6.0 * x.numel(), load().gf_mul_bf16, x.data_ptr(), other.data_ptr(), x.data_ptr(), x.numel(),
+          _stream())
+    return x
+
+
+def t5_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: int, heads: int,
+                 bias_table: torch.Tensor, bucket_of: torch.Tensor, key_mask: torch.Tensor | None = None,
+                 out: torch.Tensor | None = None) -> torch.Tensor:
+    """q: [batch*Lq, >= heads*64] view, k/v: [batch*Lk, ...]; bias_table [num_buckets, heads] bf16;
+    bucket_of int32 [Lq+Lk-1]; key_mask int32 [batch, Lk] or None."""
+    _req(q, "q"); _req(k, "k"); _req(v, "v"); _req(bias_table, "bias_table"); _req(bucket_of, "bucket_of", torch.int32)
+    Lq, Lk = q.shape[0] // batch, k.shape[0] // batch
+    if bucket_of.numel() != Lq + Lk - 1 or bias_table.shape[1] != heads or not bias_table.is_contiguous():
+        raise ValueError("bucket_of must have Lq+Lk-1 entries and bias_table must be contiguous [num_buckets, heads]")
+    if key_mask is not None:
+        _req(key_mask, "key_mask", torch.int32)
+        if key_mask.shape != (batch, Lk) or not key_mask.is_contiguous():
+            raise ValueError("key_mask must be contiguous [batch, Lk]")
+    if out is None:
+        out = torch.empty((batch * Lq, heads * 64), dtype=torch.bfloat16, device=q.device)
+    _call("attention_t5", 4.0 * batch * Lq * Lk * heads * 64, load().gf_t5_attention_bf16, q.data_ptr(), _ld(q),
+          k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(), _ld(out), batch, Lq, Lk, heads, 64,
+          bias_table.data_ptr(), bucket_of.data_ptr(), _ptr(key_mask), _stream())
     return out
 
 

@@ -126,6 +126,25 @@ int gf_cfg_euler_bf16(const void* posi, const void* nega, const void* latents, v
  * angles in float64, result rounded to bf16. timestep: [B] bf16 on the device (no host sync). */
 int gf_timestep_embedding_bf16(const void* timestep, void* out, int B, int dim, void* stream);
 
+/* ---- umT5 prompt encoder pieces (diffsynth/models/wan_video_text_encoder.py; its linears are gf_gemm_bf16) ----------
+ * gf_embedding_bf16: out[r, :] = table[ids[r], :] (token_embedding, :236); ids are int64 on the device.
+ * gf_t5_rmsnorm_bf16: T5LayerNorm (:18-30), y = bf16(x * rsqrt(mean(x^2) + eps)) * weight, out of place, d % 8 == 0.
+ * gf_mul_bf16: y = a * b elementwise (fc1(x) * gelu(gate(x)), :95-100); y may alias a or b.
+ * gf_t5_attention_bf16: T5Attention.forward (:47-78) for `batch` sequences: softmax(q k^T + pos_bias + mask) v per head,
+ *   no 1/sqrt(d) scaling, head_dim 64, Lk <= 512.  Row b*L + i of Q/K/V/O is token i of sequence b, head h at columns
+ *   [64 h, 64 h + 64).  pos_bias[h, i, j] = bias_table[bucket_of[j - i + Lq - 1] * heads + h] with bias_table the
+ *   [num_buckets, heads] bf16 weight of T5RelativeEmbedding (:136-175) and bucket_of the int32 [Lq + Lk - 1] bucket
+ *   index per relative position (host-built with the reference's formula); key_mask: [batch, Lk] int32, 0 = padding
+ *   (filled with finfo(bf16).min like :66-70), or NULL. */
+int gf_embedding_bf16(const long long* ids, const void* table, void* out, int rows, int dim, long long vocab,
+                      void* stream);
+int gf_t5_rmsnorm_bf16(const void* x, long long ldx, void* y, long long ldy, int rows, int d, const void* weight,
+                       float eps, void* stream);
+int gf_mul_bf16(const void* a, const void* b, void* y, long long n, void* stream);
+int gf_t5_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                         void* O, long long ldo, int batch, int Lq, int Lk, int heads, int head_dim,
+                         const void* bias_table, const int* bucket_of, const int* key_mask, void* stream);
+
 /* Ulysses layout helpers (replace the head<->sequence reshuffles inside xfuser's long-context attention called at
  * diffsynth/distributed/xdit_context_parallel.py:121-126).
  * pack:   x[rows, heads*head_dim] (pitch ldx) -> out[P][rows][ldo], destination rank p receives heads

@@ -213,12 +213,39 @@ def gen_mask(ns):
     torch.save(out, GOLDEN / "image_condition.pt")
 
 
+def gen_umt5():
+    """N4: the reference WanTextEncoder (eval mode) on seeded weights, fp32 and bf16, with a padding mask; plus the
+    prompter's zeroing of the positions past the prompt length (wan_prompter.py:105-108)."""
+    from . import umt5_oracle as U
+    te = ref_shim.load_module("diffsynth.models.wan_video_text_encoder")
+    cfgs = {"tiny": dict(vocab=97, dim=256, dim_attn=256, dim_ffn=512, num_heads=4, num_layers=2, num_buckets=32)}
+    out = {}
+    with torch.no_grad():
+        for name, c in cfgs.items():
+            sd = U.random_state_dict(seed=0, **c)
+            ids, mask = U.synthetic_prompt(c["vocab"], 2, 48, (48, 19), seed=1)
+            m = te.WanTextEncoder(shared_pos=False, dropout=0.1, **c).eval()
+            m.load_state_dict(sd, strict=True)
+            ref32 = m(ids, mask)
+            mb = te.WanTextEncoder(shared_pos=False, dropout=0.1, **c).eval()
+            mb.load_state_dict(sd, strict=True)
+            mb = mb.to(torch.bfloat16)
+            refbf = mb(ids, mask)
+            assert torch.equal(ref32, U.encoder(sd, ids, mask, num_heads=c["num_heads"], num_layers=c["num_layers"],
+                                                num_buckets=c["num_buckets"]))
+            out[name] = dict(cfg=c, weight_seed=0, prompt_seed=1, batch=2, L=48, valid=(48, 19), out_fp32=ref32,
+                             out_bf16=refbf, buckets=m.blocks[0].pos_embedding._relative_position_bucket(
+                                 torch.arange(48).unsqueeze(0) - torch.arange(48).unsqueeze(1)).to(torch.int32))
+            print("umt5", name, tuple(ref32.shape), "fp32-vs-bf16 relL2", O.rel_l2(refbf, ref32))
+    torch.save(out, GOLDEN / "umt5.pt")
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     ns = ref_shim.load()
     import sys
-    what = sys.argv[1:] or ["scheduler", "dit", "control", "mask"]
+    what = sys.argv[1:] or ["scheduler", "dit", "control", "mask", "umt5"]
     if "scheduler" in what:
         gen_scheduler(ns)
     if "dit" in what:
@@ -227,6 +254,8 @@ def main():
         gen_control_channels()
     if "mask" in what:
         gen_mask(ns)
+    if "umt5" in what:
+        gen_umt5()
 
 
 if __name__ == "__main__":

@@ -96,6 +96,15 @@ def load():
     return ns
 
 
+def load_module(name: str):
+    """Import one reference module by dotted name (e.g. diffsynth.models.wan_video_text_encoder)."""
+    if not available():
+        raise RuntimeError(f"reference not found at {REFERENCE_ROOT}")
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    return _import_with_stubs(name)
+
+
 def load_dataset_module():
     if not available():
         raise RuntimeError(f"reference not found at {REFERENCE_ROOT}")

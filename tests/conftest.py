@@ -39,3 +39,9 @@ def lib():
     from goal_force_b200 import build, capi
     build.build()
     return capi.load()
+
+
+@pytest.fixture(scope="module")
+def capi(lib):
+    from goal_force_b200 import capi as c
+    return c

@@ -18,12 +18,6 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-@pytest.fixture(scope="module")
-def capi(lib):
-    from goal_force_b200 import capi as c
-    return c
-
-
 @pytest.mark.parametrize("cta_group", [1, 2])
 @pytest.mark.parametrize("shape", [(128, 256, 64), (1, 5120, 256), (300, 512, 320), (1000, 768, 144), (120, 64, 256),
                                    (2050, 1536, 1536)])
