@@ -83,6 +83,8 @@ def parse():
     ap.add_argument("--controlnet-layers", type=int, default=CONTROLNET_LAYERS)
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="Ulysses exchange at N > 1: fused peer-memory stores (default) or NCCL all-to-all")
+    ap.add_argument("--controlnet-stream", default="auto", choices=["auto", "on", "off"],
+                    help="ControlNet branch on a second stream next to the trunk (auto: on for N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-kernel table to stderr")
@@ -213,7 +215,7 @@ def workload_config(args, n):
     return {"workload": "configs[1]: Wan2.2 I2V A14B high-noise expert, one denoise step (= one DiT forward), Goal "
                         "Force mode (10-block ControlNet, target-force control latents), 81x480x832 = 32760 tokens",
             "tokens": FRAMES_LAT * (H_LAT // 2) * (W_LAT // 2), "trunk_blocks": args.layers,
-            "controlnet_blocks": args.controlnet_layers, "parallelism": f"ulysses_sp{n}_{args.transport}" if n > 1 else "single_gpu",
+            "controlnet_blocks": args.controlnet_layers, "controlnet_stream": args.controlnet_stream, "parallelism": f"ulysses_sp{n}_{args.transport}" if n > 1 else "single_gpu",
             "l2": "per-step working set (35 GB of weights + 3 GB of activations) is far larger than the 126 MB L2; "
                   "no explicit flush"}
 
@@ -253,7 +255,8 @@ def run_ours(args, emit):
         return model_fn_wan_video(dit=dit, controlnet=cn, latents=inp["latents"], timestep=inp["timestep"],
                                   context=inp["context"], y=inp["y"],
                                   control_signal_video_latents=inp["control_signal_video_latents"],
-                                  sequence_parallel=sp)
+                                  sequence_parallel=sp,
+                                  controlnet_stream={"auto": None, "on": True, "off": False}[args.controlnet_stream])
 
     def barrier():
         if world > 1:

@@ -9,7 +9,7 @@ returned as an (F, H, W, 3) bf16 tensor in [0, 1].  In the reference this runs o
 (`__getitem__`), once per CSV row, before the pipeline is called; it stays host code here.  All frames of a moving
 blob are produced by one vectorised torch expression instead of a per-frame Python loop; the arithmetic per
 element (int grid -> fp32 subtract, square, add, divide by 2 r^2, exp) is unchanged, so the bf16 result is
-bit-identical (tests/test_control_channels.py checks SHA-256 digests produced by the reference's own class).
+bit-identical (tests/test_host_logic_cpu.py and tests/test_jobs_cpu.py check SHA-256 digests produced by the reference's own class).
 """
 from __future__ import annotations
 

@@ -129,11 +129,13 @@ class _Workspace:
 _WORKSPACES: dict = {}
 
 
-def _workspace(L: int, cfg: DiTConfig, device) -> _Workspace:
-    key = (L, cfg.dim, cfg.ffn_dim, str(device))
+def _workspace(L: int, cfg: DiTConfig, device, slot: int = 0) -> _Workspace:
+    """slot 0: trunk (and everything on the caller's stream); slot 1: the ControlNet branch when it runs on its own
+    stream next to the trunk."""
+    key = (L, cfg.dim, cfg.ffn_dim, str(device), slot)
     ws = _WORKSPACES.get(key)
     if ws is None:
-        if len(_WORKSPACES) > 4:
+        if len(_WORKSPACES) > 6:
             _WORKSPACES.clear()
         ws = _Workspace(L, cfg, device)
         _WORKSPACES[key] = ws
@@ -244,25 +246,28 @@ class SequenceParallel:
         n = L // self.size
         return slice(self.rank * n, (self.rank + 1) * n)
 
-    def buffers(self, Ll: int, d: int, device):
-        key = (Ll, d, str(device))
+    def buffers(self, Ll: int, d: int, device, slot: int = 0):
+        key = (Ll, d, str(device), slot)
         b = self._bufs.get(key)
         if b is None:
             P = self.size
             bf = dict(dtype=torch.bfloat16, device=device)
             b = (torch.empty((P, Ll, 3 * d // P), **bf), torch.empty((P * Ll, 3 * d // P), **bf),
                  torch.empty((P * Ll, d // P), **bf), torch.empty((P, Ll, d // P), **bf))
-            self._bufs = {key: b}
+            self._bufs = {k: v for k, v in self._bufs.items() if k[:3] == key[:3]}
+            self._bufs[key] = b
         return b
 
-    def peer_exchange(self, Ll: int, d: int, device) -> PeerExchange:
-        key = (Ll, d, str(device))
+    def peer_exchange(self, Ll: int, d: int, device, slot: int = 0) -> PeerExchange:
+        """One set of peer buffers per (token count, stream slot): the trunk and a ControlNet branch running next to it
+        on a second stream exchange through separate buffers and flags."""
+        key = (Ll, d, str(device), slot)
         ex = self._peer.get(key)
         if ex is None:
-            for old in self._peer.values():
-                old.close()
+            for k in [k for k in self._peer if k[:3] != key[:3]]:      # token count changed: tear the old ones down
+                self._peer.pop(k).close()
             ex = PeerExchange(self.dist, self.group, self.rank, self.size, Ll, d, device)
-            self._peer = {key: ex}
+            self._peer[key] = ex
         return ex
 
     def check(self) -> None:
@@ -279,12 +284,12 @@ class SequenceParallel:
             raise ValueError(f"{heads} heads do not divide over {self.size} ranks")
         return heads // self.size
 
-    def self_attention(self, qkv: torch.Tensor, heads: int, out: torch.Tensor) -> None:
+    def self_attention(self, qkv: torch.Tensor, heads: int, out: torch.Tensor, slot: int = 0) -> None:
         """NCCL transport. qkv: [L/P, 3*d] (q|k|v, already normed + roped) -> out [L/P, d]."""
         P, Ll = self.size, qkv.shape[0]
         d = qkv.shape[1] // 3
         hp = self._check_heads(heads)
-        send, recv, o_full, o_recv = self.buffers(Ll, d, qkv.device)
+        send, recv, o_full, o_recv = self.buffers(Ll, d, qkv.device, slot)
         w = hp * 128
         for s in range(3):
             capi.ulysses_pack(qkv[:, s * d:(s + 1) * d], heads, 128, P, out=send[:, :, s * w:], out_pitch=3 * w)
@@ -294,13 +299,13 @@ class SequenceParallel:
         capi.ulysses_unpack(o_recv, Ll, heads, 128, P, out=out)
 
     def self_attention_fused(self, qkv: torch.Tensor, norm_q: torch.Tensor, norm_k: torch.Tensor, eps: float,
-                             cos_sin: torch.Tensor, heads: int) -> torch.Tensor:
+                             cos_sin: torch.Tensor, heads: int, slot: int = 0) -> torch.Tensor:
         """Peer transport. qkv: [L/P, 3*d] straight out of the QKV GEMM (NOT yet normed). Returns the [L/P, d]
         attention output (a view of the peer-visible buffer, valid until the next call)."""
         P, Ll = self.size, qkv.shape[0]
         d = qkv.shape[1] // 3
         hp = self._check_heads(heads)
-        ex = self.peer_exchange(Ll, d, qkv.device)
+        ex = self.peer_exchange(Ll, d, qkv.device, slot)
         w = ex.w
         capi.qkv_rmsnorm_rope_scatter(qkv, norm_q, norm_k, eps=eps, cos_sin=cos_sin, head_dim=128,
                                       recv_ptrs=ex.recv_ptrs, n_peers=P, rank=self.rank, ld_recv=3 * w)
@@ -314,7 +319,7 @@ class SequenceParallel:
 
 def run_block(bw: _Block, cfg: DiTConfig, x: torch.Tensor, ctx_kv: torch.Tensor, mod: torch.Tensor,
               cos_sin: torch.Tensor, ws: _Workspace, sp: SequenceParallel | None = None,
-              x_in: torch.Tensor | None = None) -> None:
+              x_in: torch.Tensor | None = None, slot: int = 0) -> None:
     """DiTBlock.forward (wan_video_dit.py:214-230) on [L, dim] tokens: in place on x, or from x_in into x (x_in is
     left untouched: the first residual GEMM reads it and writes x).
     mod: [6, dim] = modulation + t_mod (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp);
@@ -327,13 +332,13 @@ def run_block(bw: _Block, cfg: DiTConfig, x: torch.Tensor, ctx_kv: torch.Tensor,
     capi.layernorm(src, eps=eps, shift=mod[0], scale=mod[1], out=h)
     capi.gemm(h, bw.wqkv, bw.bqkv, out=qkv)
     if sp is not None and sp.size > 1 and sp.transport == "peer":
-        attn = sp.self_attention_fused(qkv, bw.norm_q, bw.norm_k, eps, cos_sin, H)
+        attn = sp.self_attention_fused(qkv, bw.norm_q, bw.norm_k, eps, cos_sin, H, slot)
     else:
         capi.qk_rmsnorm_rope_(qkv, bw.norm_q, bw.norm_k, eps=eps, cos_sin=cos_sin, head_dim=128)
         if sp is None or sp.size == 1:
             capi.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], H, out=ao)
         else:
-            sp.self_attention(qkv, H, ao)
+            sp.self_attention(qkv, H, ao, slot)
         attn = ao
     capi.gemm(attn, bw.wo, bw.bo, epi=capi.GF_EPI_GATE_RES, gate=mod[2], residual=src, out=x)
     # --- cross attention
@@ -593,6 +598,18 @@ class ControlNetB200:
         return kvs
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = str(device)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = st
+    return st
+
+
 _CONVERTED: dict = {}      # id(reference module) -> (weakref, fingerprint, converted)
 _DEFAULT_SP: list = []
 
@@ -659,14 +676,18 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
                        sliding_window_size=None, sliding_window_stride=None, cfg_merge=False,
                        use_gradient_checkpointing=False, use_gradient_checkpointing_offload=False,
                        control_camera_latents_input=None, fuse_vae_embedding_in_latents=False, controlnet=None,
-                       sequence_parallel: SequenceParallel | None = None, _recompute_step_invariants: bool = False,
-                       **kwargs):
+                       sequence_parallel: SequenceParallel | None = None, controlnet_stream: bool | None = None,
+                       _recompute_step_invariants: bool = False, **kwargs):
     """Drop-in for pipe.model_fn (src/goal_force/wan_video_new.py:1349-1591), goal-force configuration.
 
     Same keyword surface as the reference; extra keywords are accepted and ignored (the pipeline passes its whole
     shared-input dict). Options that select other Wan variants raise NotImplementedError instead of silently
     computing something else. Returns a new (B, out_dim, F, H, W) bf16 tensor; inputs are not modified.
     `dit` / `controlnet` may be WanModelB200 / ControlNetB200 or the reference nn.Modules (converted on first use).
+    `controlnet_stream`: run the ControlNet branch on a second CUDA stream next to the trunk (the branch
+    never reads the noisy latents; the trunk only needs state i after its own block i).  None = on under sequence
+    parallelism, where one branch's exchange waits are filled by the other branch's kernels, off on a single GPU
+    (every kernel fills the GPU there, the two streams would only interleave).  Results are bit-identical either way.
     """
     for name, val in (("motion_controller", motion_controller if motion_bucket_id is not None else None),
                       ("vace_context", vace_context), ("audio_embeds", audio_embeds),
@@ -709,7 +730,7 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
         cos_sin = dit.rope(f, h, w, sp)
         ws = _workspace(x.shape[0], cfg, dit.device)
 
-        states = None
+        states, side, cn_events = None, None, []
         use_cn = controlnet is not None and not controlnet.is_noop
         if use_cn:                                                                              # :1489-1522
             csl = kwargs.get("control_signal_video_latents", None)
@@ -724,21 +745,46 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
             # ControlNet blocks share t_mod with the trunk but carry their own modulation tables
             cn_tab = capi.add_rows(controlnet.block_mod, t_mod_flat).view(controlnet.num_layers, 6, cfg.dim)
             states = ws.cn_states(controlnet.num_layers)       # block i: state i-1 (or the patch tokens) -> state i
-            for i, bw in enumerate(controlnet.blocks):
-                with capi.nvtx_range(f"controlnet.block{i}"):
-                    run_block(bw, cfg, states[i], cn_kv[i], cn_tab[i], cos_sin, ws, sp, x_in=s)
-                s = states[i]
+            side = None
+            if controlnet_stream if controlnet_stream is not None else sp is not None:
+                side = _side_stream(dit.device)
+            if side is None:
+                for i, bw in enumerate(controlnet.blocks):
+                    with capi.nvtx_range(f"controlnet.block{i}"):
+                        run_block(bw, cfg, states[i], cn_kv[i], cn_tab[i], cos_sin, ws, sp, x_in=s)
+                    s = states[i]
+            else:
+                # second stream, second workspace and (under sequence parallelism) second set of exchange buffers;
+                # one event per ControlNet block tells the trunk that state i is complete
+                main = torch.cuda.current_stream()
+                ws_cn = _workspace(x.shape[0], cfg, dit.device, slot=1)
+                side.wait_stream(main)
+                cn_events = []
+                with torch.cuda.stream(side):
+                    for i, bw in enumerate(controlnet.blocks):
+                        with capi.nvtx_range(f"controlnet.block{i}"):
+                            run_block(bw, cfg, states[i], cn_kv[i], cn_tab[i], cos_sin, ws_cn, sp, x_in=s, slot=1)
+                        s = states[i]
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        cn_events.append(ev)
 
         for i, bw in enumerate(dit.blocks):                                                     # :1540-1570
             with capi.nvtx_range(f"trunk.block{i}"):
                 run_block(bw, cfg, x, ctx_kv[i], block_tab[i], cos_sin, ws, sp)
             if use_cn:
+                if side is not None:
+                    j = i if controlnet.stride is None else (i // controlnet.stride if i % controlnet.stride == 0 else -1)
+                    if 0 <= j < len(cn_events):
+                        torch.cuda.current_stream().wait_event(cn_events[j])
                 if controlnet.stride is not None:
                     if i % controlnet.stride == 0 and i // controlnet.stride < len(states):
                         capi.add_(x, states[i // controlnet.stride])
                 elif i < controlnet.num_layers:
                     capi.gemm(states[i], controlnet.zero_w[i], controlnet.zero_b[i], epi=capi.GF_EPI_GATE_RES,
                               gate=None, residual=x, out=x)
+        if use_cn and side is not None:
+            torch.cuda.current_stream().wait_stream(side)      # the next call may reuse the branch's buffers
         tok = dit.head_tokens(x, head_tab)                                                      # :1581
         if sp is not None:                                                                      # :1582-1585
             full = torch.empty((L, tok.shape[1]), dtype=torch.bfloat16, device=dit.device)

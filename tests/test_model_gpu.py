@@ -274,3 +274,28 @@ def test_cuda_graph_replay_equals_eager():
     assert gfn.captures == 1 and gfn.replays == 3
     after = capi.ctx_stats()
     assert after["tmap_hits"] > before["tmap_hits"] and after["tmap_entries"] > 0
+
+
+def test_controlnet_on_second_stream_is_bit_identical():
+    """the ControlNet branch never reads the noisy latents, so it may run on its own stream next to the trunk
+    (per-block events hand the states over).  Same kernels, same operands: bit-identical, also for the strided inject
+    and across repeated calls that reuse the branch's workspace."""
+    from goal_force_b200.wan_dit import ControlNetB200, WanModelB200, model_fn_wan_video
+    cfg = O.DiTConfig(dim=1536, in_dim=36, ffn_dim=4096, out_dim=16, text_dim=256, freq_dim=256, eps=1e-6,
+                      num_heads=12, num_layers=4)
+    pc = _prod_cfg(cfg)
+    dit = WanModelB200(pc, O.random_state_dict(cfg, seed=80))
+    csd = O.random_controlnet_state_dict(cfg, 2, seed=81)
+    for stride in (None, 2):
+        cn = ControlNetB200(pc, csd, 2, stride=stride)
+        outs = {}
+        for k in range(2):
+            inp = O.synthetic_inputs(cfg, 3, 16, 24, seed=90 + k, ctx_len=64, ctx_valid=16, timestep=950.0)
+            bf = {n: v.to("cuda", torch.bfloat16) for n, v in inp.items()}
+            kw = dict(dit=dit, controlnet=cn, latents=bf["latents"], timestep=bf["timestep"], context=bf["context"],
+                      y=bf["y"], control_signal_video_latents=bf["control_signal_video_latents"])
+            a = model_fn_wan_video(controlnet_stream=False, **kw)
+            b = model_fn_wan_video(controlnet_stream=True, **kw)
+            assert torch.equal(a, b), (stride, k)
+            outs[k] = a
+        assert not torch.equal(outs[0], outs[1])

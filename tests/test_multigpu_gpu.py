@@ -44,6 +44,8 @@ def _worker(rank, world, port, mode, transport, ret, shape=(4, 40, 52)):
             multi = model_fn_wan_video(sequence_parallel=par.sp, **kw)
             multi2 = model_fn_wan_video(sequence_parallel=par.sp, **kw)      # buffers / epochs reused
             assert torch.equal(multi, multi2)
+            # default under SP: ControlNet branch on its own stream with its own exchange buffers; same result without
+            assert torch.equal(model_fn_wan_video(sequence_parallel=par.sp, controlnet_stream=False, **kw), multi)
             if transport == "peer":    # the reference's flag alone shards over the default group
                 assert torch.equal(model_fn_wan_video(use_unified_sequence_parallel=True, **kw), multi)
             ok = bool(torch.equal(single, multi))
