@@ -309,11 +309,16 @@ def gemm_tuning(group_m: int = 0) -> None:
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, out: torch.Tensor | None = None,
-              scale: float | None = None) -> torch.Tensor:
-    """q: [Lq, >=heads*128] view, k/v: [Lk, ...] views (row pitch taken from stride(0))."""
+              scale: float | None = None, kv_len: int | None = None) -> torch.Tensor:
+    """q: [Lq, >=heads*128] view, k/v: [Lk, ...] views (row pitch taken from stride(0)).  kv_len < Lk attends only to
+    the first kv_len keys (zero-padded token tails under sequence parallelism)."""
     _req(q, "q"); _req(k, "k"); _req(v, "v")
     head_dim = 128
     Lq, Lk = q.shape[0], k.shape[0]
+    if kv_len is not None:
+        if not 0 < kv_len <= Lk:
+            raise ValueError("kv_len must be in (0, number of key rows]")
+        Lk = kv_len
     if out is None:
         out = torch.empty((Lq, heads * head_dim), dtype=torch.bfloat16, device=q.device)
     if scale is None:
@@ -580,11 +585,16 @@ def qkv_rmsnorm_rope_scatter(qkv: torch.Tensor, weight_q: torch.Tensor, weight_k
 
 
 def attention_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, out_ptrs: ctypes.Array,
-                      n_peers: int, ldo: int, rows_per_peer: int, col_offset: int, scale: float | None = None) -> None:
+                      n_peers: int, ldo: int, rows_per_peer: int, col_offset: int, scale: float | None = None,
+                      kv_len: int | None = None) -> None:
     """attention() whose output rows are stored into their owners' [rows_per_peer, ldo] buffers (Ulysses return)."""
     _req(q, "q"); _req(k, "k"); _req(v, "v")
     head_dim = 128
     Lq, Lk = q.shape[0], k.shape[0]
+    if kv_len is not None:
+        if not 0 < kv_len <= Lk:
+            raise ValueError("kv_len must be in (0, number of key rows]")
+        Lk = kv_len
     if scale is None:
         scale = head_dim ** -0.5
     _call("attention_self", 4.0 * Lq * Lk * heads * head_dim, load().gf_attention_scatter_bf16, ctx(), q.data_ptr(),

@@ -54,7 +54,8 @@ def _check_cfg(cfg: DiTConfig) -> None:
         raise ValueError("dim must be a multiple of 256 and ffn_dim of 32")
 
 
-def rope_cos_sin(head_dim: int, f: int, h: int, w: int, device, token_slice: slice | None = None) -> torch.Tensor:
+def rope_cos_sin(head_dim: int, f: int, h: int, w: int, device, token_slice: slice | None = None,
+                 pad_rows_to: int | None = None) -> torch.Tensor:
     """(cos, sin) table [f*h*w, head_dim/2, 2] fp32 for the kernels, from the reference's float64 recipe
     (precompute_freqs_cis_3d, wan_video_dit.py:75-89, assembled as in :380-384): per-axis angles pos * theta^(-2j/dim)
     with dims head_dim-2*(head_dim//3), head_dim//3, head_dim//3; cos/sin taken in float64, rounded once to fp32."""
@@ -73,6 +74,8 @@ def rope_cos_sin(head_dim: int, f: int, h: int, w: int, device, token_slice: sli
     ], dim=-1).reshape(f * h * w, head_dim // 2)
     if token_slice is not None:
         ang = ang[token_slice]
+    if pad_rows_to is not None and ang.shape[0] < pad_rows_to:          # identity rotation for padding rows
+        ang = torch.cat([ang, ang.new_zeros(pad_rows_to - ang.shape[0], ang.shape[1])], 0)
     return torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).float().contiguous().to(device)
 
 
@@ -240,11 +243,26 @@ class SequenceParallel:
         self._bufs: dict = {}
         self._peer: dict = {}
 
+    def rows_per_rank(self, L: int) -> int:
+        return -(-L // self.size)
+
     def token_slice(self, L: int) -> slice:
-        if L % self.size:
-            raise ValueError(f"token count {L} must divide evenly over {self.size} sequence-parallel ranks")
-        n = L // self.size
-        return slice(self.rank * n, (self.rank + 1) * n)
+        """This rank's contiguous token range.  When L does not divide, the ranges are ceil(L/P) long and the tail of
+        the last ranks is padding (the reference pads the chunked sequence with zeros as well,
+        diffsynth/distributed/xdit_context_parallel.py:15-40,60-66; there the pad rows are attended as keys, here
+        they are masked out, so SP(P) stays identical to the unsharded forward)."""
+        n = self.rows_per_rank(L)
+        return slice(min(self.rank * n, L), min((self.rank + 1) * n, L))
+
+    def shard_rows(self, t: torch.Tensor, L: int) -> torch.Tensor:
+        """rows of this rank out of a [L, ...] tensor, zero-padded to rows_per_rank(L)."""
+        n = self.rows_per_rank(L)
+        part = t[self.token_slice(L)]
+        if part.shape[0] == n:
+            return part.contiguous()
+        out = t.new_zeros((n,) + tuple(t.shape[1:]))
+        out[:part.shape[0]] = part
+        return out
 
     def buffers(self, Ll: int, d: int, device, slot: int = 0):
         key = (Ll, d, str(device), slot)
@@ -284,7 +302,8 @@ class SequenceParallel:
             raise ValueError(f"{heads} heads do not divide over {self.size} ranks")
         return heads // self.size
 
-    def self_attention(self, qkv: torch.Tensor, heads: int, out: torch.Tensor, slot: int = 0) -> None:
+    def self_attention(self, qkv: torch.Tensor, heads: int, out: torch.Tensor, slot: int = 0,
+                       kv_len: int | None = None) -> None:
         """NCCL transport. qkv: [L/P, 3*d] (q|k|v, already normed + roped) -> out [L/P, d]."""
         P, Ll = self.size, qkv.shape[0]
         d = qkv.shape[1] // 3
@@ -294,12 +313,12 @@ class SequenceParallel:
         for s in range(3):
             capi.ulysses_pack(qkv[:, s * d:(s + 1) * d], heads, 128, P, out=send[:, :, s * w:], out_pitch=3 * w)
         self.dist.all_to_all_single(recv.view(P, Ll, 3 * w), send, group=self.group)
-        capi.attention(recv[:, :w], recv[:, w:2 * w], recv[:, 2 * w:], hp, out=o_full)
+        capi.attention(recv[:, :w], recv[:, w:2 * w], recv[:, 2 * w:], hp, out=o_full, kv_len=kv_len)
         self.dist.all_to_all_single(o_recv, o_full.view(P, Ll, w), group=self.group)
         capi.ulysses_unpack(o_recv, Ll, heads, 128, P, out=out)
 
     def self_attention_fused(self, qkv: torch.Tensor, norm_q: torch.Tensor, norm_k: torch.Tensor, eps: float,
-                             cos_sin: torch.Tensor, heads: int, slot: int = 0) -> torch.Tensor:
+                             cos_sin: torch.Tensor, heads: int, slot: int = 0, kv_len: int | None = None) -> torch.Tensor:
         """Peer transport. qkv: [L/P, 3*d] straight out of the QKV GEMM (NOT yet normed). Returns the [L/P, d]
         attention output (a view of the peer-visible buffer, valid until the next call)."""
         P, Ll = self.size, qkv.shape[0]
@@ -312,14 +331,14 @@ class SequenceParallel:
         ex.barrier()                                   # every rank's q|k|v has landed here
         r = ex.recv
         capi.attention_scatter(r[:, :w], r[:, w:2 * w], r[:, 2 * w:], hp, out_ptrs=ex.ao_ptrs, n_peers=P, ldo=d,
-                               rows_per_peer=Ll, col_offset=self.rank * w)
+                               rows_per_peer=Ll, col_offset=self.rank * w, kv_len=kv_len)
         ex.barrier()                                   # every rank's heads have landed in my ao
         return ex.ao
 
 
 def run_block(bw: _Block, cfg: DiTConfig, x: torch.Tensor, ctx_kv: torch.Tensor, mod: torch.Tensor,
               cos_sin: torch.Tensor, ws: _Workspace, sp: SequenceParallel | None = None,
-              x_in: torch.Tensor | None = None, slot: int = 0) -> None:
+              x_in: torch.Tensor | None = None, slot: int = 0, kv_len: int | None = None) -> None:
     """DiTBlock.forward (wan_video_dit.py:214-230) on [L, dim] tokens: in place on x, or from x_in into x (x_in is
     left untouched: the first residual GEMM reads it and writes x).
     mod: [6, dim] = modulation + t_mod (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp);
@@ -332,13 +351,13 @@ def run_block(bw: _Block, cfg: DiTConfig, x: torch.Tensor, ctx_kv: torch.Tensor,
     capi.layernorm(src, eps=eps, shift=mod[0], scale=mod[1], out=h)
     capi.gemm(h, bw.wqkv, bw.bqkv, out=qkv)
     if sp is not None and sp.size > 1 and sp.transport == "peer":
-        attn = sp.self_attention_fused(qkv, bw.norm_q, bw.norm_k, eps, cos_sin, H, slot)
+        attn = sp.self_attention_fused(qkv, bw.norm_q, bw.norm_k, eps, cos_sin, H, slot, kv_len)
     else:
         capi.qk_rmsnorm_rope_(qkv, bw.norm_q, bw.norm_k, eps=eps, cos_sin=cos_sin, head_dim=128)
         if sp is None or sp.size == 1:
             capi.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], H, out=ao)
         else:
-            sp.self_attention(qkv, H, ao, slot)
+            sp.self_attention(qkv, H, ao, slot, kv_len)
         attn = ao
     capi.gemm(attn, bw.wo, bw.bo, epi=capi.GF_EPI_GATE_RES, gate=mod[2], residual=src, out=x)
     # --- cross attention
@@ -426,7 +445,8 @@ class WanModelB200:
         t = self._rope_cache.get(key)
         if t is None:
             sl = sp.token_slice(f * h * w) if sp is not None and sp.size > 1 else None
-            t = rope_cos_sin(self.cfg.head_dim, f, h, w, self.device, sl)
+            t = rope_cos_sin(self.cfg.head_dim, f, h, w, self.device, sl,
+                             sp.rows_per_rank(f * h * w) if sl is not None else None)
             self._rope_cache = {key: t}
         return t
 
@@ -725,8 +745,11 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
         ctx_kv = ctx_entry[1]
         x, (f, h, w) = dit.patchify(lat, yb)                                                    # :1464
         L = f * h * w
+        kv_len = None
         if sp is not None:
-            x = x[sp.token_slice(L)].contiguous()                                               # :1526-1531
+            x = sp.shard_rows(x, L)                                                             # :1526-1531
+            if L % sp.size:
+                kv_len = L                       # padded tail rows exist on the last rank(s): never attend to them
         cos_sin = dit.rope(f, h, w, sp)
         ws = _workspace(x.shape[0], cfg, dit.device)
 
@@ -740,7 +763,7 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
             if s.shape[0] != L:
                 raise ValueError("control latents and latents have different token counts")
             if sp is not None:
-                s = s[sp.token_slice(L)]
+                s = sp.shard_rows(s, L)
             cn_kv = controlnet.context_kv(ctx_entry, cache=use_cache)
             # ControlNet blocks share t_mod with the trunk but carry their own modulation tables
             cn_tab = capi.add_rows(controlnet.block_mod, t_mod_flat).view(controlnet.num_layers, 6, cfg.dim)
@@ -751,7 +774,7 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
             if side is None:
                 for i, bw in enumerate(controlnet.blocks):
                     with capi.nvtx_range(f"controlnet.block{i}"):
-                        run_block(bw, cfg, states[i], cn_kv[i], cn_tab[i], cos_sin, ws, sp, x_in=s)
+                        run_block(bw, cfg, states[i], cn_kv[i], cn_tab[i], cos_sin, ws, sp, x_in=s, kv_len=kv_len)
                     s = states[i]
             else:
                 # second stream, second workspace and (under sequence parallelism) second set of exchange buffers;
@@ -763,7 +786,8 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
                 with torch.cuda.stream(side):
                     for i, bw in enumerate(controlnet.blocks):
                         with capi.nvtx_range(f"controlnet.block{i}"):
-                            run_block(bw, cfg, states[i], cn_kv[i], cn_tab[i], cos_sin, ws_cn, sp, x_in=s, slot=1)
+                            run_block(bw, cfg, states[i], cn_kv[i], cn_tab[i], cos_sin, ws_cn, sp, x_in=s, slot=1,
+                                      kv_len=kv_len)
                         s = states[i]
                         ev = torch.cuda.Event()
                         ev.record(side)
@@ -771,7 +795,7 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
 
         for i, bw in enumerate(dit.blocks):                                                     # :1540-1570
             with capi.nvtx_range(f"trunk.block{i}"):
-                run_block(bw, cfg, x, ctx_kv[i], block_tab[i], cos_sin, ws, sp)
+                run_block(bw, cfg, x, ctx_kv[i], block_tab[i], cos_sin, ws, sp, kv_len=kv_len)
             if use_cn:
                 if side is not None:
                     j = i if controlnet.stride is None else (i // controlnet.stride if i % controlnet.stride == 0 else -1)
@@ -787,8 +811,8 @@ def model_fn_wan_video(dit=None, motion_controller=None, vace=None, latents=None
             torch.cuda.current_stream().wait_stream(side)      # the next call may reuse the branch's buffers
         tok = dit.head_tokens(x, head_tab)                                                      # :1581
         if sp is not None:                                                                      # :1582-1585
-            full = torch.empty((L, tok.shape[1]), dtype=torch.bfloat16, device=dit.device)
+            full = torch.empty((sp.rows_per_rank(L) * sp.size, tok.shape[1]), dtype=torch.bfloat16, device=dit.device)
             sp.dist.all_gather_into_tensor(full, tok, group=sp.group)
-            tok = full
+            tok = full[:L]                                        # strips the padding rows (reference :1584-1585)
         outs.append(dit.unpatchify(tok, (f, h, w)))                                             # :1590
     return torch.stack(outs, 0)

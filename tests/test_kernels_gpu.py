@@ -210,3 +210,18 @@ def test_timestep_embedding(capi):
         got = capi.timestep_embedding(t, 256)
         ref = O.sinusoidal_embedding_1d(256, t)
         assert (got != ref).float().mean() < 0.02 and float((got.float() - ref.float()).abs().max()) < 8e-3
+
+
+def test_attention_kv_len_masks_padded_keys(capi, attn_variant):
+    """kv_len < rows of K/V: the trailing (padding) keys are ignored -- same result as slicing them away."""
+    torch.manual_seed(7)
+    Lq, Lk, h = 333, 300, 2
+    q = torch.randn(Lq, h * 128, device="cuda").bfloat16()
+    k = torch.randn(Lk, h * 128, device="cuda").bfloat16()
+    v = torch.randn(Lk, h * 128, device="cuda").bfloat16()
+    for n in (299, 241, 80, 1):
+        a = capi.attention(q, k, v, h, kv_len=n)
+        b = capi.attention(q, k[:n], v[:n], h)
+        assert torch.equal(a, b), n
+    with pytest.raises(ValueError):
+        capi.attention(q, k, v, h, kv_len=301)

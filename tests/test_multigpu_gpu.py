@@ -103,3 +103,12 @@ def test_ulysses_sp8_long_sequence_bit_identical(lib):
     """BASELINE configs[4]: 81 x 720 x 1280 = 75,600 tokens over 8 GPUs (9,450 tokens and 5 heads per rank), fused
     peer exchange, against the same forward on one GPU."""
     _run("sp", "peer", 8, shape=(21, 90, 160))
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_ulysses_token_count_not_divisible(lib, transport):
+    """Reference pad path (diffsynth/distributed/xdit_context_parallel.py:15-40,60-66): latent 3 x 10 x 18 -> 135 tokens
+    over 2 ranks = 68 + 67 (+1 zero row).  The padding row is masked out of the keys, so the result still equals the
+    unsharded forward bit for bit."""
+    _run("sp", transport, 2, shape=(3, 10, 18))
