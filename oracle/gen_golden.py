@@ -240,12 +240,44 @@ def gen_umt5():
     torch.save(out, GOLDEN / "umt5.pt")
 
 
+def gen_vae():
+    """N2: the reference Wan2.1 video VAE (VideoVAE_ chunked encode / decode and WanVideoVAE's tiled wrappers) on
+    seeded weights at a CPU-sized width (dim 32 instead of 96; same topology), fp32.  Also asserts that the full-clip
+    formulation of oracle/wan_vae_oracle.py equals the reference's chunk-by-chunk walk."""
+    from . import wan_vae_oracle as V
+    vae = ref_shim.load_module("diffsynth.models.wan_video_vae")
+    dim = 32
+    sd = V.random_state_dict(dim=dim, seed=0)
+    wrap = vae.WanVideoVAE(z_dim=16)
+    wrap.model = vae.VideoVAE_(dim=dim, z_dim=16).eval().requires_grad_(False)
+    wrap.model.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(1)
+    z = torch.randn(1, 16, 3, 4, 6, generator=g)
+    video = torch.randn(1, 3, 9, 32, 48, generator=g).clamp_(-1, 1)
+    z_big = torch.randn(1, 16, 2, 7, 9, generator=g)
+    out = {"dim": dim, "weight_seed": 0, "z": z, "video": video, "z_big": z_big}
+    with torch.no_grad():
+        out["decode"] = wrap.model.decode(z, wrap.scale)
+        out["encode"] = wrap.model.encode(video, wrap.scale)
+        out["tiled_decode"] = wrap.tiled_decode(z_big, "cpu", (4, 5), (3, 3))
+        out["tiled_encode"] = wrap.tiled_encode(out["tiled_decode"], "cpu", (32, 40), (24, 24))
+        assert O.rel_l2(V.decode(sd, z, dim=dim), out["decode"]) < 1e-5
+        assert O.rel_l2(V.encode(sd, video, dim=dim), out["encode"]) < 1e-5
+        assert O.rel_l2(V.tiled_decode(sd, z_big, (4, 5), (3, 3), dim=dim), out["tiled_decode"]) < 1e-5
+        assert O.rel_l2(V.tiled_encode(sd, out["tiled_decode"], (32, 40), (24, 24), dim=dim), out["tiled_encode"]) < 1e-5
+    out = {k: (v.to(torch.float16) if isinstance(v, torch.Tensor) and k in ("decode", "tiled_decode") else v)
+           for k, v in out.items()}
+    for k in ("decode", "encode", "tiled_decode", "tiled_encode"):
+        print("vae", k, tuple(out[k].shape))
+    torch.save(out, GOLDEN / "vae.pt")
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     ns = ref_shim.load()
     import sys
-    what = sys.argv[1:] or ["scheduler", "dit", "control", "mask", "umt5"]
+    what = sys.argv[1:] or ["scheduler", "dit", "control", "mask", "umt5", "vae"]
     if "scheduler" in what:
         gen_scheduler(ns)
     if "dit" in what:
@@ -256,6 +288,8 @@ def main():
         gen_mask(ns)
     if "umt5" in what:
         gen_umt5()
+    if "vae" in what:
+        gen_vae()
 
 
 if __name__ == "__main__":
