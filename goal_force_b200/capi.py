@@ -18,8 +18,9 @@ GF_EPI_BIAS = 0
 GF_EPI_BIAS_GELU = 1
 GF_EPI_BIAS_SILU = 2
 GF_EPI_GATE_RES = 3
+GF_EPI_F32 = 4
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _ERRORS = {-1: "GF_ERR_BAD_ARG", -2: "GF_ERR_NO_DRIVER", -3: "GF_ERR_TMAP", -4: "GF_ERR_UNSUPPORTED"}
 
@@ -49,6 +50,15 @@ SIGNATURES = {
     "gf_t5_rmsnorm_bf16": [_p, _ll, _p, _ll, _i, _i, _p, _f, _p],
     "gf_mul_bf16": [_p, _p, _p, _ll, _p],
     "gf_t5_attention_bf16": [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "gf_conv3d_cl_bf16": [_p, _p, _ll, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _ll, _i, _i, _i,
+                          _p, _ll, _p, _ll, _p, _i, _i, _p],
+    "gf_vae_rmsnorm_bf16": [_p, _ll, _p, _ll, _ll, _i, _p, _i, _p],
+    "gf_vae_upsample2x_bf16": [_p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p],
+    "gf_softmax_f32_bf16": [_p, _ll, _p, _ll, _i, _i, _i, _f, _p],
+    "gf_vae_planes_to_cl_bf16": [_p, _ll, _i, _p, _ll, _i, _p, _p, _i, _p],
+    "gf_vae_cl_to_planes_bf16": [_p, _ll, _ll, _i, _p, _p, _p, _i, _p],
+    "gf_vae_blend_bf16": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p],
+    "gf_vae_blend_finish_bf16": [_p, _ll, _i, _i, _p, _i, _p],
     "gf_peer_alloc": [ctypes.POINTER(ctypes.c_void_p), _ll],
     "gf_peer_free": [_p],
     "gf_peer_export": [_p, _p],
@@ -487,6 +497,141 @@ def t5_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: in
           k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(), _ld(out), batch, Lq, Lk, heads, 64,
           bias_table.data_ptr(), bucket_of.data_ptr(), _ptr(key_mask), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ Wan VAE pieces
+def gemm_f32(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, n: int | None = None, cta_group: int = 2) -> torch.Tensor:
+    """out[M, n] (fp32, pitch out.stride(0)) = a[M,K] @ w[:n,K]^T.  `n` (multiple of 32) may exceed the rows the caller
+    cares about when the memory behind w is valid (padded score columns of the VAE attention)."""
+    _req(a, "a"); _req(w, "w"); _req(out, "out", torch.float32)
+    M, K = a.shape
+    N = w.shape[0] if n is None else n
+    if out.shape[0] != M or out.shape[1] < N:
+        raise ValueError("gemm_f32: out too small")
+    _call("gemm", 2.0 * M * N * K, load().gf_gemm_bf16, ctx(), a.data_ptr(), _ld(a), w.data_ptr(), _ld(w), out.data_ptr(),
+          _ld(out), M, N, K, None, GF_EPI_F32, None, None, 0, cta_group, _stream())
+    return out
+
+
+def conv3d_cl(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, *, kernel, stride=(1, 1, 1), pad=(0, 0, 0),
+              out_dims=None, out: torch.Tensor | None = None, residual: torch.Tensor | None = None,
+              norm_out: torch.Tensor | None = None, gamma: torch.Tensor | None = None, silu: bool = True,
+              cout: int | None = None, ncthw: bool = False, want_raw: bool = True):
+    """x: [T, H, W, Cin] channels-last view (position pitch x.stride(2)); w: [Cout, taps*Cin]; see gf_conv3d_cl_bf16.
+    Returns (Y or None, Y2 or None)."""
+    _req(x, "x"); _req(w, "w")
+    T, H, W, Cin = x.shape
+    ldx = x.stride(2)
+    if x.stride(1) != W * ldx or x.stride(0) != H * W * ldx:
+        raise ValueError("conv3d_cl: x must be a dense [T, H, W] grid of rows")
+    kt, kh, kw = kernel
+    Cout = w.shape[0] if cout is None else cout
+    if w.shape[1] != kt * kh * kw * Cin or not w.is_contiguous():
+        raise ValueError(f"conv3d_cl: weight {tuple(w.shape)} does not match taps*Cin = {kt * kh * kw * Cin}")
+    To, Ho, Wo = out_dims if out_dims is not None else (T, H, W)
+    cs = (Cout + 7) // 8 * 8
+    if ncthw:
+        if out is None:
+            out = torch.empty((Cout, To, Ho, Wo), dtype=torch.bfloat16, device=x.device)
+        ldy = 0
+    else:
+        if out is None and want_raw:
+            out = torch.empty((To, Ho, Wo, cs), dtype=torch.bfloat16, device=x.device)
+        ldy = out.stride(2) if out is not None else 0
+    if gamma is not None and norm_out is None:
+        norm_out = torch.empty((To, Ho, Wo, cs), dtype=torch.bfloat16, device=x.device)
+    for nme, t in (("bias", bias), ("residual", residual), ("gamma", gamma), ("out", out), ("norm_out", norm_out)):
+        if t is not None:
+            _req(t, nme)
+    _call("conv3d", 2.0 * To * Ho * Wo * Cout * kt * kh * kw * Cin, load().gf_conv3d_cl_bf16, ctx(), x.data_ptr(), ldx, T,
+          H, W, Cin, w.data_ptr(), Cout, kt, kh, kw, stride[0], stride[1], stride[2], pad[0], pad[1], pad[2], _ptr(bias),
+          _ptr(out), ldy, To, Ho, Wo, _ptr(residual), residual.stride(2) if residual is not None else 0,
+          _ptr(norm_out), norm_out.stride(2) if norm_out is not None else 0, _ptr(gamma), 1 if silu else 0,
+          1 if ncthw else 0, _stream())
+    return out, norm_out
+
+
+def vae_rmsnorm(x: torch.Tensor, gamma: torch.Tensor, *, silu: bool, out: torch.Tensor | None = None) -> torch.Tensor:
+    """x: [..., C] rows with a uniform pitch (x.stride(-2)); RMS_norm over C (+ SiLU)."""
+    _req(x, "x"); _req(gamma, "gamma")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _call("vae_rowwise", 4.0 * rows * C, load().gf_vae_rmsnorm_bf16, x.data_ptr(), x.stride(-2), out.data_ptr(),
+          out.stride(-2), rows, C, gamma.data_ptr(), 1 if silu else 0, _stream())
+    return out
+
+
+def vae_upsample2x(first: torch.Tensor, rest: torch.Tensor | None, F: int, H: int, W: int, C: int,
+                   out: torch.Tensor | None = None) -> torch.Tensor:
+    _req(first, "first")
+    if rest is not None:
+        _req(rest, "rest")
+    if out is None:
+        out = torch.empty((F, 2 * H, 2 * W, C), dtype=torch.bfloat16, device=first.device)
+    _call("vae_rowwise", 10.0 * F * H * W * C, load().gf_vae_upsample2x_bf16, first.data_ptr(), first.stride(-2),
+          _ptr(rest), rest.stride(-2) if rest is not None else 0, out.data_ptr(), out.stride(-2), F, H, W, C, _stream())
+    return out
+
+
+def softmax_f32(S: torch.Tensor, P: torch.Tensor, L: int, Lp: int, scale: float) -> torch.Tensor:
+    _req(S, "S", torch.float32); _req(P, "P")
+    _call("vae_rowwise", 6.0 * S.shape[0] * L, load().gf_softmax_f32_bf16, S.data_ptr(), S.stride(0), P.data_ptr(),
+          P.stride(0), S.shape[0], L, Lp, scale, _stream())
+    return P
+
+
+def vae_planes_to_cl(src: torch.Tensor, Cp: int, *, mean: torch.Tensor | None = None,
+                     inv_std: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """src: (C, T, H, W) contiguous bf16 -> [T, H, W, Cp] channels-last (zero-padded channels)."""
+    _req(src, "src")
+    if not src.is_contiguous():
+        raise ValueError("vae_planes_to_cl: src must be contiguous")
+    C, T, H, W = src.shape
+    if out is None:
+        out = torch.empty((T, H, W, Cp), dtype=torch.bfloat16, device=src.device)
+    mode = 0 if mean is None else 1
+    if mode:
+        _req(mean, "mean", torch.float32); _req(inv_std, "inv_std", torch.float32)
+    _call("vae_rowwise", 2.0 * T * H * W * (C + Cp), load().gf_vae_planes_to_cl_bf16, src.data_ptr(), T * H * W, C,
+          out.data_ptr(), out.stride(2), Cp, _ptr(mean), _ptr(inv_std), mode, _stream())
+    return out
+
+
+def vae_cl_to_planes(src: torch.Tensor, C: int, *, mean: torch.Tensor | None = None,
+                     inv_std: torch.Tensor | None = None) -> torch.Tensor:
+    """src: [T, H, W, >=C] channels-last -> (C, T, H, W) bf16."""
+    _req(src, "src")
+    T, H, W, _ = src.shape
+    out = torch.empty((C, T, H, W), dtype=torch.bfloat16, device=src.device)
+    mode = 0 if mean is None else 1
+    if mode:
+        _req(mean, "mean", torch.float32); _req(inv_std, "inv_std", torch.float32)
+    _call("vae_rowwise", 4.0 * T * H * W * C, load().gf_vae_cl_to_planes_bf16, src.data_ptr(), src.stride(2), T * H * W, C,
+          out.data_ptr(), _ptr(mean), _ptr(inv_std), mode, _stream())
+    return out
+
+
+def vae_blend_(values: torch.Tensor, tile: torch.Tensor, mask: torch.Tensor, h0: int, w0: int) -> None:
+    """values (C, T, H, W) += tile (C, T, th, tw) * mask (th, tw), reference rounding."""
+    _req(values, "values"); _req(tile, "tile"); _req(mask, "mask")
+    if not (values.is_contiguous() and tile.is_contiguous() and mask.is_contiguous()):
+        raise ValueError("vae_blend_: contiguous tensors required")
+    C, T, H, W = values.shape
+    th, tw = tile.shape[2], tile.shape[3]
+    _call("vae_rowwise", 6.0 * tile.numel(), load().gf_vae_blend_bf16, values.data_ptr(), C, T, H, W, tile.data_ptr(),
+          th, tw, h0, w0, mask.data_ptr(), _stream())
+
+
+def vae_blend_finish_(values: torch.Tensor, weight: torch.Tensor | None, clamp: bool) -> torch.Tensor:
+    _req(values, "values")
+    C, T, H, W = values.shape
+    if weight is not None:
+        _req(weight, "weight")
+    _call("vae_rowwise", 4.0 * values.numel(), load().gf_vae_blend_finish_bf16, values.data_ptr(), C * T, H, W,
+          _ptr(weight), 1 if clamp else 0, _stream())
+    return values
 
 
 # ------------------------------------------------------------------------------------------------ peer memory

@@ -17,6 +17,11 @@ int gf_num_sms();
 int gf_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
                          uint32_t box_inner, uint32_t box_outer);
 
+// 4-D bf16 tensor map with 128-byte swizzle: dims[0] is the contiguous one, strides_bytes[i] is the pitch of dims[i+1]
+// (multiples of 16), box[0] * 2 == 128.  Used by the implicit-GEMM convolution (gf_conv.cu); not cached.
+int gf_make_tmap_4d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                         const uint32_t box[4]);
+
 // Tensor map for (base, dims, pitch, box): looked up in / inserted into the context's cache when ctx != nullptr,
 // otherwise encoded into `scratch`.  Returns nullptr and sets *rc on failure.  A tensor map depends only on the
 // address and the geometry, never on the contents, so a cached entry stays valid when a buffer is freed and another

@@ -1,0 +1,364 @@
+// gf_conv.cu -- implicit-GEMM 3-D convolution for the Wan video VAE on sm_100a (tcgen05 / TMEM / TMA).
+//
+//   Y[to, ho, wo, :] = epilogue( sum_{dt,dh,dw,ci} Wt[co, (dt,dh,dw), ci] * X[to*st + dt - pt, ho*sh + dh - ph, wo*sw + dw - pw, ci] )
+//
+// Replaces CausalConv3d (diffsynth/models/wan_video_vae.py:33-52), the Conv2d of Resample (:92-119) and the strided
+// time_conv (:104-119) of the reference.  The clip is channels-last ([T][H][W][C] bf16), so the GEMM is
+//   M = To*Ho*Wo output positions,  N = Cout,  K = taps * Cin,
+// and nothing is ever gathered into an im2col buffer: for every tap the TMA producer loads the SAME 4-D tensor map at
+// a shifted coordinate.  Rows of an M tile are a BH x BW patch of one output frame (BH*BW = 128); box elements outside
+// the clip (negative t: the causal front padding; h, w outside: the spatial zero padding) are zero-filled by TMA.
+// A strided convolution reads through one tensor map per input parity (base pointer offset, doubled pitches), so the
+// box stays dense in the map's own coordinates.
+//
+// Structure = gf_gemm.cu's single-CTA form: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue,
+// two 256-column accumulator stages.  A k-block is 64 channels of one tap; for Cin % 64 != 0 the last block of a tap
+// issues only the valid 16-wide MMAs (the TMA box is zero-filled, the weights beside it are never multiplied).
+//
+// Epilogue (per output position, fp32 accumulator):
+//   v  = bf16(acc + bias)                      ; v = bf16(v + R) when a residual is given (ResidualBlock tail, :296-301)
+//   Y  = v                                     (channels-last, or (C, T, H, W) for the 3-channel head)
+//   Y2 = silu(v / max(|v|_2, 1e-12) * sqrt(C) * gamma)   (the NEXT layer's RMS_norm + SiLU, :55-70,283-288) when the
+//        whole channel row lives in one tile (Cout <= 256); two passes over the accumulator in TMEM.
+#include "gf_ptx.cuh"
+#include "gf_api_internal.h"
+
+namespace gf {
+
+constexpr int CONV_BM = 128;
+constexpr int CONV_BK = 64;
+constexpr int CONV_THREADS = 192;
+constexpr int CONV_MAX_TAPS = 27;
+constexpr int CONV_MAX_STAGES = 8;
+constexpr int CONV_A_BYTES = CONV_BM * CONV_BK * 2;   // 16 KB
+constexpr int CONV_SMEM_BUDGET = 200 * 1024;
+
+struct ConvMaps {
+  CUtensorMap a[4];   // input clip, one map per (h, w) parity of a strided convolution
+  CUtensorMap b;      // weights [Cout][taps * Cin]
+};
+
+struct ConvParams {
+  int To, Ho, Wo;
+  int Cin;              // multiple of 8
+  int Cout;             // real output channels
+  int cout_store;       // Cout rounded up to 8 (channels-last rows are written in 16-byte vectors)
+  int ntaps;
+  int st;               // temporal stride
+  int bw_shift;         // BW = 1 << bw_shift, BH = 128 >> bw_shift
+  int nWt, nHt;
+  int BN, num_n_tiles;
+  int stages;
+  int ncthw;            // 1: Y is (Cout, To, Ho, Wo)
+  int silu;
+  signed char tap_map[CONV_MAX_TAPS], tap_dt[CONV_MAX_TAPS], tap_dh[CONV_MAX_TAPS], tap_dw[CONV_MAX_TAPS];
+  __nv_bfloat16* Y; long long ldy;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* R; long long ldr;
+  __nv_bfloat16* Y2; long long ldy2;
+  const __nv_bfloat16* gamma;
+};
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+gf_conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = CONV_A_BYTES + (uint32_t)p.BN * 128u;
+  const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (CONV_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * CONV_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * CONV_MAX_STAGES + 2 + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * CONV_MAX_STAGES + 4);
+  auto smem_a = [&](int s) { return smem_base + s * stage_bytes; };
+  auto smem_b = [&](int s) { return smem_base + s * stage_bytes + CONV_A_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int tiles_per_frame = p.nWt * p.nHt;
+  const int num_m_tiles = p.To * tiles_per_frame;
+  const int num_tiles = num_m_tiles * p.num_n_tiles;
+  const int num_cb = (p.Cin + CONV_BK - 1) / CONV_BK;
+  const int BW = 1 << p.bw_shift, BH = CONV_BM >> p.bw_shift;
+
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 4);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<1>(tmem_ptr_smem, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
+        const int tt = mt / tiles_per_frame;
+        const int rem = mt - tt * tiles_per_frame;
+        const int ht = rem / p.nWt, wt = rem - ht * p.nWt;
+        const int h0 = ht * BH, w0 = wt * BW, n0 = nt * p.BN;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const CUtensorMap* am = &maps.a[p.tap_map[tap]];
+          const int ct = tt * p.st + p.tap_dt[tap], ch = h0 + p.tap_dh[tap], cw = w0 + p.tap_dw[tap];
+          for (int cb = 0; cb < num_cb; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+            tma_load_4d(smem_a(stage), am, full_bar(stage), cb * CONV_BK, cw, ch, ct);
+            tma_load_2d(smem_b(stage), &maps.b, full_bar(stage), tap * p.Cin + cb * CONV_BK, n0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc = idesc_bf16(CONV_BM, (uint32_t)p.BN, 0, 0);
+      constexpr uint64_t dbase = smem_desc_base(/*sbo=*/1024, /*lbo=*/16);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        uint32_t first = 0;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int cb = 0; cb < num_cb; ++cb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_a(stage), b_addr = smem_b(stage);
+            const int kvalid = min(CONV_BK, p.Cin - cb * CONV_BK);
+            const int nk = (kvalid + 15) >> 4;
+            for (int k = 0; k < nk; ++k) {
+              umma_ss<1>(d_tmem, smem_desc(dbase, a_addr + k * 32), smem_desc(dbase, b_addr + k * 32), idesc, first);
+              first = 1u;
+            }
+            tc_commit(empty_bar(stage));
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        tc_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int q = warp & 3;
+    const int lane = (int)lane_id();
+    const int r = q * 32 + lane;
+    const int hh = r >> p.bw_shift, ww = r & (BW - 1);
+    const long long frame = (long long)p.Ho * p.Wo;
+    const bool fused_norm = p.Y2 != nullptr;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
+      const int tt = mt / tiles_per_frame;
+      const int rem = mt - tt * tiles_per_frame;
+      const int ht = rem / p.nWt, wt = rem - ht * p.nWt;
+      const int h = ht * BH + hh, w = wt * BW + ww, n0 = nt * p.BN;
+      const bool ok = h < p.Ho && w < p.Wo;
+      const long long pos = (long long)tt * frame + (long long)h * p.Wo + w;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * 256;
+      float ss = 0.0f;
+      float rinv = 0.0f;
+      const int passes = fused_norm ? 2 : 1;
+      for (int pass = 0; pass < passes; ++pass) {
+#pragma unroll 1
+        for (int c = 0; c < p.BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.cout_store) break;                 // uniform over the CTA
+          uint32_t v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int cg = col0 + g * 8;
+            if (cg >= p.cout_store) break;
+            uint4 bv = make_uint4(0, 0, 0, 0), rv = make_uint4(0, 0, 0, 0);
+            if (p.bias) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + cg));
+            if (p.R && ok) rv = *reinterpret_cast<const uint4*>(p.R + pos * p.ldr + cg);
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              x[2 * j] = round_bf16(__uint_as_float(v[g * 8 + 2 * j]) + bf16_lo(bw[j]));
+              x[2 * j + 1] = round_bf16(__uint_as_float(v[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
+              if (p.R) {
+                x[2 * j] = round_bf16(x[2 * j] + bf16_lo(rw[j]));
+                x[2 * j + 1] = round_bf16(x[2 * j + 1] + bf16_hi(rw[j]));
+              }
+            }
+            if (pass == 0) {
+              if (fused_norm) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (cg + j < p.Cout) ss += x[j] * x[j];
+              }
+              if (p.Y && ok) {
+                if (p.ncthw) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (cg + j < p.Cout) p.Y[(long long)(cg + j) * p.To * frame + pos] = __float2bfloat16_rn(x[j]);
+                } else {
+                  *reinterpret_cast<uint4*>(p.Y + pos * p.ldy + cg) =
+                      make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                                 pack_bf16x2(x[6], x[7]));
+                }
+              }
+            } else {
+              const uint4 gv = __ldg(reinterpret_cast<const uint4*>(p.gamma + cg));
+              const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+              float y[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                y[2 * j] = x[2 * j] * rinv * bf16_lo(gw[j]);
+                y[2 * j + 1] = x[2 * j + 1] * rinv * bf16_hi(gw[j]);
+              }
+              if (p.silu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = y[j] / (1.0f + __expf(-y[j]));
+              }
+              if (ok)
+                *reinterpret_cast<uint4*>(p.Y2 + pos * p.ldy2 + cg) =
+                    make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                               pack_bf16x2(y[6], y[7]));
+            }
+          }
+        }
+        if (pass == 0 && fused_norm) rinv = sqrtf((float)p.Cout) / fmaxf(sqrtf(ss), 1e-12f);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+static inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+}  // namespace gf
+
+extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int T, int H, int W, int Cin, const void* Wt,
+                                 int Cout, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw,
+                                 const void* bias, void* Y, long long ldy, int To, int Ho, int Wo, const void* R,
+                                 long long ldr, void* Y2, long long ldy2, const void* gamma, int silu, int out_ncthw,
+                                 void* stream) {
+  using namespace gf;
+  (void)ctx;
+  if (!X || !Wt || (!Y && !Y2) || T <= 0 || H <= 0 || W <= 0 || To <= 0 || Ho <= 0 || Wo <= 0) return GF_ERR_BAD_ARG;
+  if (Cin <= 0 || (Cin % 8) || (ldx % 8) || ldx < Cin || Cout <= 0) return GF_ERR_BAD_ARG;
+  if (kt < 1 || kh < 1 || kw < 1 || kt * kh * kw > CONV_MAX_TAPS) return GF_ERR_UNSUPPORTED;
+  if (st < 1 || sh < 1 || sh > 2 || sw != sh) return GF_ERR_UNSUPPORTED;
+  if (pt < 0 || ph < 0 || pw < 0 || pt > 8 || ph > 8 || pw > 8) return GF_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wt) | reinterpret_cast<uintptr_t>(Y) |
+       reinterpret_cast<uintptr_t>(Y2) | reinterpret_cast<uintptr_t>(R) | reinterpret_cast<uintptr_t>(bias) |
+       reinterpret_cast<uintptr_t>(gamma)) & 15)
+    return GF_ERR_BAD_ARG;
+  const int cout_store = (Cout + 7) & ~7;
+  if (!out_ncthw && Y && ((ldy % 8) || ldy < cout_store)) return GF_ERR_BAD_ARG;
+  if (out_ncthw && (R || Y2)) return GF_ERR_UNSUPPORTED;
+  if (R && ((ldr % 8) || ldr < cout_store)) return GF_ERR_BAD_ARG;
+  if (Y2 && (!gamma || (ldy2 % 8) || ldy2 < cout_store)) return GF_ERR_BAD_ARG;
+
+  ConvParams p{};
+  p.To = To; p.Ho = Ho; p.Wo = Wo;
+  p.Cin = Cin; p.Cout = Cout; p.cout_store = cout_store;
+  p.ntaps = kt * kh * kw;
+  p.st = st;
+  const int cout32 = (Cout + 31) & ~31;
+  p.num_n_tiles = (cout32 + 255) / 256;
+  p.BN = (((cout32 + p.num_n_tiles - 1) / p.num_n_tiles) + 31) & ~31;
+  if (Y2 && p.num_n_tiles != 1) return GF_ERR_UNSUPPORTED;   // fused RMS_norm needs the whole channel row in one tile
+  // M-tile patch: the BW x BH (= 128) shape that wastes the fewest rows on this frame size
+  long long best = -1;
+  for (int s = 3; s <= 7; ++s) {
+    const int bw = 1 << s, bh = 128 >> s;
+    const long long cover = (long long)((Wo + bw - 1) / bw) * bw * ((Ho + bh - 1) / bh) * bh;
+    if (best < 0 || cover < best) { best = cover; p.bw_shift = s; }
+  }
+  const int BW = 1 << p.bw_shift, BH = 128 >> p.bw_shift;
+  p.nWt = (Wo + BW - 1) / BW;
+  p.nHt = (Ho + BH - 1) / BH;
+  const int stage_bytes = CONV_A_BYTES + p.BN * 128;
+  p.stages = CONV_SMEM_BUDGET / stage_bytes;
+  if (p.stages > CONV_MAX_STAGES) p.stages = CONV_MAX_STAGES;
+  p.ncthw = out_ncthw; p.silu = silu;
+  p.Y = reinterpret_cast<__nv_bfloat16*>(Y); p.ldy = ldy;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.R = reinterpret_cast<const __nv_bfloat16*>(R); p.ldr = ldr;
+  p.Y2 = reinterpret_cast<__nv_bfloat16*>(Y2); p.ldy2 = ldy2;
+  p.gamma = reinterpret_cast<const __nv_bfloat16*>(gamma);
+
+  // taps: input index = out*stride + d - pad = stride*(out + floor(e/stride)) + (e mod stride), e = d - pad
+  int tap = 0;
+  for (int dt = 0; dt < kt; ++dt)
+    for (int dh = 0; dh < kh; ++dh)
+      for (int dw = 0; dw < kw; ++dw, ++tap) {
+        const int eh = dh - ph, ew = dw - pw;
+        const int oh = floor_div(eh, sh), ow = floor_div(ew, sw);
+        const int par_h = eh - oh * sh, par_w = ew - ow * sw;
+        p.tap_map[tap] = (signed char)(par_h * sw + par_w);
+        p.tap_dt[tap] = (signed char)(dt - pt);
+        p.tap_dh[tap] = (signed char)oh;
+        p.tap_dw[tap] = (signed char)ow;
+      }
+
+  ConvMaps maps;
+  const char* xb = reinterpret_cast<const char*>(X);
+  int rc = 0;
+  for (int par_h = 0; par_h < sh; ++par_h)
+    for (int par_w = 0; par_w < sw; ++par_w) {
+      if (par_h >= H || par_w >= W) return GF_ERR_BAD_ARG;
+      const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)((W - par_w + sw - 1) / sw), (uint64_t)((H - par_h + sh - 1) / sh),
+                                (uint64_t)T};
+      const uint64_t strides[3] = {(uint64_t)ldx * 2 * sw, (uint64_t)ldx * 2 * W * sh, (uint64_t)ldx * 2 * W * H};
+      const uint32_t box[4] = {(uint32_t)CONV_BK, (uint32_t)BW, (uint32_t)BH, 1u};
+      rc = gf_make_tmap_4d_bf16(&maps.a[par_h * sw + par_w], xb + ((long long)par_h * W + par_w) * ldx * 2, dims,
+                                strides, box);
+      if (rc) return rc;
+    }
+  for (int i = sh * sw; i < 4; ++i) maps.a[i] = maps.a[0];
+  rc = gf_make_tmap_2d_bf16(&maps.b, Wt, (uint64_t)p.ntaps * Cin, (uint64_t)Cout, (uint64_t)p.ntaps * Cin, CONV_BK,
+                            (uint32_t)p.BN);
+  if (rc) return rc;
+
+  const int smem = p.stages * stage_bytes + 1024 + 256;
+  static bool configured[64] = {};
+  if (int e = gf_set_smem_once(configured, reinterpret_cast<const void*>(gf_conv3d_kernel), 227 * 1024)) return e;
+  const long long tiles = (long long)To * p.nWt * p.nHt * p.num_n_tiles;
+  int grid = gf_num_sms();
+  if (grid <= 0) return GF_ERR_NO_DRIVER;
+  if (grid > tiles) grid = (int)tiles;
+  gf_conv3d_kernel<<<grid, CONV_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, p);
+  return (int)cudaGetLastError();
+}

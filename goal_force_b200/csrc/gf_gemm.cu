@@ -8,6 +8,7 @@
 //   EPI_BIAS        : C = acc + bias                                   (q/k/v projections, text/time MLPs)
 //   EPI_BIAS_GELU   : C = gelu_tanh(acc + bias)                        (ffn.0 + nn.GELU(approximate='tanh'))
 //   EPI_BIAS_SILU   : C = silu(acc + bias)                             (time_embedding.0 + SiLU)
+//   EPI_F32         : C = acc + bias, stored as fp32 (ldc in floats)  (VAE attention scores, wan_video_vae.py:325-337)
 //   EPI_GATE_RES    : C = R + gate[n] * (acc + bias)  (gate==null: 1)  (o-proj / ffn.2 + GateModule, cross-attn
 //                                                                       residual, ControlNet zero-conv inject)
 // Rounding points follow eager bf16 PyTorch (linear -> bf16, gate*y -> bf16, x+.. -> bf16) so the result tracks the
@@ -189,7 +190,7 @@ gf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * GEMM_BN;
-      __nv_bfloat16* crow = p.C + (long long)row * p.ldc + n0;
+      __nv_bfloat16* crow = (EPI == GF_EPI_F32) ? p.C : p.C + (long long)row * p.ldc + n0;
       const __nv_bfloat16* rrow = (EPI == GF_EPI_GATE_RES) ? p.R + (long long)row * p.ldr + n0 : nullptr;
 #pragma unroll 1
       for (int c = 0; c < GEMM_BN / 32; ++c) {
@@ -197,6 +198,23 @@ gf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld32(t_addr + c * 32, v);
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
+        if constexpr (EPI == GF_EPI_F32) {
+          // fp32 result (attention scores of the VAE's single-head attention, softmax'd by gf_softmax_f32_bf16)
+          if (col0 < p.N && row_ok) {
+            float* frow = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              float4 o;
+              o.x = __uint_as_float(v[g * 4 + 0]); o.y = __uint_as_float(v[g * 4 + 1]);
+              o.z = __uint_as_float(v[g * 4 + 2]); o.w = __uint_as_float(v[g * 4 + 3]);
+              if (p.bias) {
+                o.x += __bfloat162float(p.bias[col0 + g * 4 + 0]); o.y += __bfloat162float(p.bias[col0 + g * 4 + 1]);
+                o.z += __bfloat162float(p.bias[col0 + g * 4 + 2]); o.w += __bfloat162float(p.bias[col0 + g * 4 + 3]);
+              }
+              *reinterpret_cast<float4*>(frow + g * 4) = o;
+            }
+          }
+        } else
         if (col0 < p.N) {                           // N is a multiple of 32 on every call site (checked on host)
           uint32_t outw[16];
 #pragma unroll
@@ -287,6 +305,7 @@ static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, con
     case GF_EPI_BIAS_GELU: return launch_gemm<kCG, GF_EPI_BIAS_GELU>(a, b, p, s);
     case GF_EPI_BIAS_SILU: return launch_gemm<kCG, GF_EPI_BIAS_SILU>(a, b, p, s);
     case GF_EPI_GATE_RES: return launch_gemm<kCG, GF_EPI_GATE_RES>(a, b, p, s);
+    case GF_EPI_F32: return launch_gemm<kCG, GF_EPI_F32>(a, b, p, s);
     default: return GF_ERR_BAD_ARG;
   }
 }
@@ -298,7 +317,7 @@ extern "C" int gf_gemm_bf16(gf_ctx* ctx, const void* A, long long lda, const voi
                             int cta_group, void* stream) {
   using namespace gf;
   if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0) return GF_ERR_BAD_ARG;
-  if ((N % 32) || (K % 8) || (lda % 8) || (ldw % 8) || (ldc % 8)) return GF_ERR_BAD_ARG;
+  if ((N % 32) || (K % 8) || (lda % 8) || (ldw % 8) || (ldc % (epi == GF_EPI_F32 ? 4 : 8))) return GF_ERR_BAD_ARG;
   if (epi == GF_EPI_GATE_RES && (!R || (ldr % 8))) return GF_ERR_BAD_ARG;
   if (cta_group != 1 && cta_group != 2) return GF_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) & 15)

@@ -136,6 +136,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(d)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 4-D tiled load (implicit-GEMM convolution: channels x W x H x T box of a channels-last clip); coordinates are signed,
+// box elements outside the tensor read as zero -- that is the convolution's zero padding.
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* d, uint32_t bar, int32_t c0,
+                                            int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(d)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // 2-CTA variant: data lands in this CTA's smem, completion bytes go to `bar` which may live in the pair's
 // leader CTA (pass a shared::cluster address, e.g. own address with the peer bit cleared).
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const CUtensorMap* d, uint32_t bar, int32_t c0,

@@ -80,6 +80,29 @@ int gf_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uin
   return r == CUDA_SUCCESS ? 0 : GF_ERR_TMAP;
 }
 
+int gf_make_tmap_4d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                         const uint32_t box[4]) {
+  EncodeTiledFn enc = resolve_encode();
+  if (!enc) return GF_ERR_NO_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || box[0] * 2 != 128) return GF_ERR_BAD_ARG;
+  cuuint64_t d[4];
+  cuuint64_t st[3];
+  cuuint32_t bx[4], estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) {
+    if (dims[i] == 0 || box[i] == 0 || box[i] > 256) return GF_ERR_BAD_ARG;
+    d[i] = dims[i];
+    bx[i] = box[i];
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (strides_bytes[i] % 16) return GF_ERR_BAD_ARG;
+    st[i] = strides_bytes[i];
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, st, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : GF_ERR_TMAP;
+}
+
 const CUtensorMap* gf_ctx_tmap(gf_ctx* ctx, CUtensorMap* scratch, const void* base, uint64_t inner, uint64_t outer,
                                uint64_t ld, uint32_t box_inner, uint32_t box_outer, int* rc) {
   *rc = 0;

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GF_ABI_VERSION 2
+#define GF_ABI_VERSION 3
 
 #define GF_ERR_BAD_ARG (-1)      /* null pointer, misaligned pointer/pitch, unsupported size */
 #define GF_ERR_NO_DRIVER (-2)    /* cuTensorMapEncodeTiled not resolvable (no driver / no GPU) */
@@ -37,6 +37,7 @@ extern "C" {
 #define GF_EPI_BIAS_GELU 1  /* C = gelu_tanh(A.W^T + bias)          wan_video_dit.py:209-210   */
 #define GF_EPI_BIAS_SILU 2  /* C = silu(A.W^T + bias)               wan_video_dit.py:314-318   */
 #define GF_EPI_GATE_RES 3   /* C = R + gate[n]*(A.W^T + bias)       wan_video_dit.py:189-194,226-229 */
+#define GF_EPI_F32 4        /* C = A.W^T + bias stored as fp32 (ldc in floats)   wan_video_vae.py:325-337 */
 
 int gf_abi_version(void);
 
@@ -144,6 +145,54 @@ int gf_mul_bf16(const void* a, const void* b, void* y, long long n, void* stream
 int gf_t5_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
                          void* O, long long ldo, int batch, int Lq, int Lk, int heads, int head_dim,
                          const void* bias_table, const int* bucket_of, const int* key_mask, void* stream);
+
+/* ---- Wan video VAE (diffsynth/models/wan_video_vae.py) -------------------------------------------------
+ * Clips are channels-last: X[t][h][w][c] bf16 with position pitch ld* (elements, multiple of 8).
+ *
+ * gf_conv3d_cl_bf16: 3-D convolution as an implicit GEMM on the tensor cores (CausalConv3d :33-52, Resample's Conv2d
+ * :92-119 with kt = 1, the strided time_conv :104-119).
+ *   Y[to,ho,wo,co] = sum Wt[co][(dt,dh,dw)][ci] * X[to*st + dt - pt, ho*sh + dh - ph, wo*sw + dw - pw, ci]  (+ bias)
+ * Input positions outside the clip read as zero, so pt/ph/pw are the leading paddings (pt = kt-1 is the causal form)
+ * and the trailing padding follows from To/Ho/Wo.  Wt: [Cout][kt*kh*kw][Cin] bf16, Cin % 8 == 0; sh == sw in {1, 2}.
+ * R (optional): residual [To*Ho*Wo][ldr] added after the bias (ResidualBlock :296-301).
+ * Y2/gamma (optional, Cout <= 256): Y2 = act(RMS_norm(Y) * gamma) of the NEXT layer (:55-70), act = SiLU when silu != 0;
+ * Y may be NULL when only Y2 is wanted.  out_ncthw != 0: Y is (Cout, To, Ho, Wo) planes (the 3-channel decoder head).
+ * bias/gamma hold at least Cout rounded up to 8 elements. */
+int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int T, int H, int W, int Cin, const void* Wt, int Cout,
+                      int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw, const void* bias, void* Y,
+                      long long ldy, int To, int Ho, int Wo, const void* R, long long ldr, void* Y2, long long ldy2,
+                      const void* gamma, int silu, int out_ncthw, void* stream);
+
+/* RMS_norm over the channels of every position (:55-70): y = x / max(|x|_2, 1e-12) * sqrt(C) * gamma, then SiLU when
+ * silu != 0 (ResidualBlock :283-288, heads :581,801).  C % 8 == 0, C <= 1024. */
+int gf_vae_rmsnorm_bf16(const void* x, long long ldx, void* y, long long ldy, long long rows, int C, const void* gamma,
+                        int silu, void* stream);
+
+/* Nearest-exact 2x spatial upsampling of F frames (Upsample :74-80): out[f][2h+a][2w+b] = src_f[h][w].
+ * rest == NULL: src_f = first[f].  rest != NULL (upsample3d :138-160): output frame 0 reads first[0]; output frame
+ * f >= 1 reads rest[(f-1)/2] at channel offset ((f-1)%2)*C, where rest is the [.,.,.,2C] time_conv result. */
+int gf_vae_upsample2x_bf16(const void* first, long long ld_first, const void* rest, long long ld_rest, void* out,
+                           long long ldo, int F, int H, int W, int C, void* stream);
+
+/* P[r, :L] = softmax(S[r, :L] * scale) in bf16, P[r, L:Lp] = 0; S fp32 (gf_gemm_bf16 with GF_EPI_F32).  The
+ * single-head attention of AttentionBlock (:304-342) is S = q k^T, this, then P v as GEMMs. */
+int gf_softmax_f32_bf16(const float* S, long long lds, void* P, long long ldp, int rows, int L, int Lp, float scale,
+                        void* stream);
+
+/* (C, N) planes <-> channels-last rows.  planes_to_cl pads channels [C, Cp) with zeros; mode 1 applies the latent
+ * un-normalisation z / inv_std + mean of VideoVAE_.decode (:1014-1018).  cl_to_planes mode 1 applies
+ * (mu - mean) * inv_std of VideoVAE_.encode (:1003-1007).  mean / inv_std: fp32 [C] on the device. */
+int gf_vae_planes_to_cl_bf16(const void* src, long long N, int C, void* dst, long long ldo, int Cp, const float* mean,
+                             const float* inv_std, int mode, void* stream);
+int gf_vae_cl_to_planes_bf16(const void* src, long long ld, long long N, int C, void* dst, const float* mean,
+                             const float* inv_std, int mode, void* stream);
+
+/* Tile blending of WanVideoVAE.tiled_decode / tiled_encode (:1133-1153,1184-1204).
+ * blend: values[c][t][h0+y][w0+x] += tile[c][t][y][x] * mask[y][x] (bf16 rounding after the product and after the sum).
+ * blend_finish: values /= weight[h][w] (NULL: skip) and clamp to [-1, 1] when clamp != 0 (single_decode :1214-1217). */
+int gf_vae_blend_bf16(void* values, int C, int T, int H, int W, const void* tile, int th, int tw, int h0, int w0,
+                      const void* mask, void* stream);
+int gf_vae_blend_finish_bf16(void* values, long long planes, int H, int W, const void* weight, int clamp, void* stream);
 
 /* Ulysses layout helpers (replace the head<->sequence reshuffles inside xfuser's long-context attention called at
  * diffsynth/distributed/xdit_context_parallel.py:121-126).

@@ -1,0 +1,237 @@
+"""Wan video VAE on B200: the implicit-GEMM convolution and the streaming kernels against plain torch
+fp32 on the same bf16 inputs, and the whole encoder / decoder / tiling against the oracle and the reference's golden
+vectors (tests/golden/vae.pt).  Tolerance for whole-network comparisons: our distance to the fp32 oracle may not exceed
+the distance of the oracle's own bf16 run (same weights, same input) to it -- stated per test."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import wan_dit_oracle as O
+from oracle import wan_vae_oracle as V
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def _cl(x):
+    """(C, T, H, W) -> [T, H, W, C] contiguous"""
+    return x.permute(1, 2, 3, 0).contiguous()
+
+
+def _w2d(w, cinp):
+    cout, cin = w.shape[:2]
+    w = w.permute(0, 2, 3, 4, 1)
+    if cinp != cin:
+        w = F.pad(w, (0, cinp - cin))
+    return w.reshape(cout, -1).contiguous()
+
+
+CONV_CASES = [
+    # name, Cin, Cout, (T, H, W), kernel, stride, pad(leading), (residual, fused norm, ncthw)
+    ("causal333_96", 96, 96, (5, 20, 28), (3, 3, 3), (1, 1, 1), (2, 1, 1), (False, False, False)),
+    ("causal333_16_to_32", 16, 32, (3, 9, 13), (3, 3, 3), (1, 1, 1), (2, 1, 1), (False, False, False)),
+    ("causal333_8_to_96", 8, 96, (5, 16, 24), (3, 3, 3), (1, 1, 1), (2, 1, 1), (False, True, False)),
+    ("causal333_192_res_norm", 192, 192, (4, 12, 20), (3, 3, 3), (1, 1, 1), (2, 1, 1), (True, True, False)),
+    ("causal333_384_two_n_tiles", 384, 384, (3, 10, 14), (3, 3, 3), (1, 1, 1), (2, 1, 1), (True, False, False)),
+    ("causal333_192_to_384", 192, 384, (2, 8, 8), (3, 3, 3), (1, 1, 1), (2, 1, 1), (False, False, False)),
+    ("conv2d_33_pad1", 192, 96, (3, 16, 24), (1, 3, 3), (1, 1, 1), (0, 1, 1), (False, True, False)),
+    ("conv2d_33_stride2", 96, 96, (3, 16, 24), (1, 3, 3), (1, 2, 2), (0, 0, 0), (False, False, False)),
+    ("conv2d_33_stride2_odd_tiles", 64, 64, (2, 30, 52), (1, 3, 3), (1, 2, 2), (0, 0, 0), (False, True, False)),
+    ("time311_causal_to_2c", 128, 256, (4, 6, 10), (3, 1, 1), (1, 1, 1), (2, 0, 0), (False, False, False)),
+    ("time311_stride2", 192, 192, (9, 6, 10), (3, 1, 1), (2, 1, 1), (0, 0, 0), (False, False, False)),
+    ("pointwise_16", 16, 16, (3, 7, 9), (1, 1, 1), (1, 1, 1), (0, 0, 0), (False, False, False)),
+    ("head_96_to_3_ncthw", 96, 3, (5, 24, 40), (3, 3, 3), (1, 1, 1), (2, 1, 1), (False, False, True)),
+    ("wide_frame_128", 96, 96, (2, 8, 300), (3, 3, 3), (1, 1, 1), (2, 1, 1), (False, False, False)),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv3d_against_torch(capi, case):
+    name, cin, cout, (T, H, W), kernel, stride, pad, (use_res, use_norm, ncthw) = case
+    g = torch.Generator(device="cpu").manual_seed(sum(name.encode()))
+    kt, kh, kw = kernel
+    x = _bf(torch.randn(cin, T, H, W, generator=g)).cuda()
+    w = _bf(torch.randn(cout, cin, kt, kh, kw, generator=g) * (cin * kt * kh * kw) ** -0.5).cuda()
+    b = _bf(torch.randn(cout, generator=g) * 0.1).cuda()
+    # reference: explicit zero padding (leading pad as given, trailing so that the output size is what the VAE uses)
+    if stride[1] == 2:
+        Ho, Wo = H // 2, W // 2
+        xp = F.pad(x.float(), (0, 1, 0, 1, pad[0], 0))
+    else:
+        Ho, Wo = H, W
+        xp = F.pad(x.float(), (pad[2], kw - 1 - pad[2], pad[1], kh - 1 - pad[1], pad[0], 0))
+    ref = F.conv3d(xp.unsqueeze(0), w.float(), b.float(), stride=stride)[0]
+    To = ref.shape[1]
+    assert ref.shape == (cout, To, Ho, Wo)
+    ref = _bf(ref).float()
+    res = None
+    if use_res:
+        res = _bf(torch.randn(cout, To, Ho, Wo, generator=g)).cuda()
+        ref = _bf(ref + res.float()).float()
+    bias = torch.zeros((cout + 7) // 8 * 8, dtype=torch.bfloat16, device="cuda")
+    bias[:cout] = b
+    gamma = _bf(1.0 + 0.1 * torch.randn(cout, generator=g)).cuda() if use_norm else None
+    y, yn = capi.conv3d_cl(_cl(x), _w2d(w, cin), bias, kernel=kernel, stride=stride, pad=pad, out_dims=(To, Ho, Wo),
+                           residual=_cl(res) if use_res else None, gamma=gamma, silu=True, cout=cout, ncthw=ncthw)
+    torch.cuda.synchronize()
+    got = y.float() if ncthw else y.float().permute(3, 0, 1, 2)[:cout]
+    err = O.rel_l2(got, ref)
+    assert err < 3e-3, f"{name}: rel_l2 {err:.3e}, max abs {float((got - ref).abs().max()):.3e}"
+    assert float((got - ref).abs().max()) <= 0.02 * float(ref.abs().max()) + 1e-2
+    if use_norm:
+        want = F.silu(V.rms_norm(ref.unsqueeze(0), gamma.float().view(-1, 1, 1, 1))[0])
+        gotn = yn.float().permute(3, 0, 1, 2)[:cout]
+        errn = O.rel_l2(gotn, want)
+        assert errn < 6e-3, f"{name}: fused norm rel_l2 {errn:.3e}"
+        sep = capi.vae_rmsnorm(y, gamma, silu=True)
+        torch.cuda.synchronize()
+        assert O.rel_l2(sep.float(), yn.float()) < 1e-3
+
+
+def test_rowwise_kernels_against_torch(capi):
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for C in (32, 96, 192, 384):
+        x = _bf(torch.randn(5, 7, 11, C, generator=g) * 2).cuda()
+        gamma = _bf(1.0 + 0.1 * torch.randn(C, generator=g)).cuda()
+        for silu in (True, False):
+            y = capi.vae_rmsnorm(x, gamma, silu=silu)
+            want = F.normalize(x.float(), dim=-1) * C ** 0.5 * gamma.float()
+            want = F.silu(want) if silu else want
+            assert O.rel_l2(y.float(), want) < 4e-3, (C, silu)
+    # nearest-exact 2x with and without the temporal interleave
+    C, T, H, W = 32, 3, 5, 6
+    x = _bf(torch.randn(T, H, W, C, generator=g)).cuda()
+    up = capi.vae_upsample2x(x, None, T, H, W, C)
+    want = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=(2.0, 2.0), mode="nearest-exact").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), want)
+    rest = _bf(torch.randn(T - 1, H, W, 2 * C, generator=g)).cuda()
+    up3 = capi.vae_upsample2x(x, rest, 2 * T - 1, H, W, C)
+    frames = [x[0]] + [rest[i // 2, :, :, (i % 2) * C:(i % 2 + 1) * C] for i in range(2 * (T - 1))]
+    src = torch.stack(frames)
+    want3 = F.interpolate(src.permute(0, 3, 1, 2).float(), scale_factor=(2.0, 2.0), mode="nearest-exact").permute(0, 2, 3, 1)
+    assert torch.equal(up3.float(), want3)
+    # softmax of fp32 scores with a padded tail
+    L, Lp = 70, 96
+    S = torch.randn(L, Lp, generator=g).cuda() * 4
+    P = torch.empty(L, Lp, dtype=torch.bfloat16, device="cuda")
+    capi.softmax_f32(S, P, L, Lp, 0.25)
+    want = torch.softmax(S[:, :L] * 0.25, dim=-1)
+    assert O.rel_l2(P[:, :L].float(), want) < 4e-3 and float(P[:, L:].abs().max()) == 0.0
+    # layout changes and the latent affine
+    z = _bf(torch.randn(16, 3, 4, 5, generator=g)).cuda()
+    mean = torch.tensor(V.MEAN, device="cuda")
+    inv_std = (1.0 / torch.tensor(V.STD)).cuda()
+    cl = capi.vae_planes_to_cl(z, 16, mean=mean, inv_std=inv_std)
+    want = _bf(_bf(z / _bf(inv_std).view(-1, 1, 1, 1)) + _bf(mean).view(-1, 1, 1, 1))
+    assert torch.equal(cl.permute(3, 0, 1, 2), want)
+    v3 = _bf(torch.randn(3, 2, 4, 6, generator=g)).cuda()
+    cl3 = capi.vae_planes_to_cl(v3, 8)
+    assert torch.equal(cl3[..., :3].permute(3, 0, 1, 2), v3) and float(cl3[..., 3:].abs().max()) == 0.0
+    back = capi.vae_cl_to_planes(cl, 16, mean=mean, inv_std=inv_std)
+    wantb = _bf(_bf(cl.permute(3, 0, 1, 2) - _bf(mean).view(-1, 1, 1, 1)) * _bf(inv_std).view(-1, 1, 1, 1))
+    assert torch.equal(back, wantb)
+    # blending: two torch bf16 ops
+    values = _bf(torch.randn(3, 2, 10, 12, generator=g)).cuda()
+    tile = _bf(torch.randn(3, 2, 4, 5, generator=g)).cuda()
+    mask = _bf(torch.rand(4, 5, generator=g)).cuda()
+    want = values.clone()
+    want[:, :, 3:7, 2:7] += tile * mask
+    capi.vae_blend_(values, tile, mask, 3, 2)
+    assert torch.equal(values, want)
+    wgt = _bf(torch.rand(10, 12, generator=g) + 0.5).cuda()
+    wantf = (want / wgt).clamp_(-1, 1)
+    capi.vae_blend_finish_(values, wgt, clamp=True)
+    assert torch.equal(values, wantf)
+
+
+def _golden(golden_dir):
+    g = torch.load(golden_dir / "vae.pt", weights_only=False)
+    sd = V.random_state_dict(dim=g["dim"], seed=g["weight_seed"])
+    return g, sd
+
+
+def _bf16_oracle_err(fn, sd, x, want, **kw):
+    """distance of the oracle's own bf16 run (on this GPU) to the fp32 result -- the tolerance budget"""
+    sdb = {k: v.to(device="cuda", dtype=torch.bfloat16) for k, v in sd.items()}
+    with torch.no_grad():
+        return O.rel_l2(fn(sdb, x.to(device="cuda", dtype=torch.bfloat16), **kw).float().cpu(), want)
+
+
+def test_decode_and_encode_against_reference_vectors(golden_dir):
+    from goal_force_b200.wan_vae import WanVideoVAEB200
+    g, sd = _golden(golden_dir)
+    dim = g["dim"]
+    vae = WanVideoVAEB200(sd, dim=dim)
+    want = g["decode"].float()
+    got = vae._decode_clip(g["z"][0].to(device="cuda", dtype=torch.bfloat16)).float().cpu().unsqueeze(0)
+    err = O.rel_l2(got, want)
+    budget = _bf16_oracle_err(V.decode, sd, g["z"], want, dim=dim)
+    print(f"vae decode (dim {dim}): ours {err:.3e}  oracle-bf16 {budget:.3e}")
+    assert err <= max(budget, 4e-3), (err, budget)
+    want = g["encode"]
+    got = vae._encode_clip(g["video"][0].to(device="cuda", dtype=torch.bfloat16)).float().cpu().unsqueeze(0)
+    err = O.rel_l2(got, want)
+    budget = _bf16_oracle_err(V.encode, sd, g["video"], want, dim=dim)
+    print(f"vae encode (dim {dim}): ours {err:.3e}  oracle-bf16 {budget:.3e}")
+    assert err <= max(budget, 4e-3), (err, budget)
+
+
+def test_tiled_paths_against_reference_vectors(golden_dir):
+    from goal_force_b200.wan_vae import WanVideoVAEB200
+    g, sd = _golden(golden_dir)
+    dim = g["dim"]
+    vae = WanVideoVAEB200(sd, dim=dim)
+    want = g["tiled_decode"].float()
+    got = vae.decode(g["z_big"].to(torch.bfloat16), "cuda", tiled=True, tile_size=(4, 5), tile_stride=(3, 3)).float().cpu()
+    err = O.rel_l2(got, want)
+    budget = _bf16_oracle_err(V.tiled_decode, sd, g["z_big"], want, tile_size=(4, 5), tile_stride=(3, 3), dim=dim)
+    print(f"vae tiled decode: ours {err:.3e}  oracle-bf16 {budget:.3e}")
+    assert got.shape == want.shape and err <= max(budget, 5e-3), (err, budget)
+    assert float(got.abs().max()) <= 1.0
+    video = want.to(torch.bfloat16)
+    wante = g["tiled_encode"]
+    gote = vae.encode(video, "cuda", tiled=True, tile_size=(4, 5), tile_stride=(3, 3)).float().cpu()
+    erre = O.rel_l2(gote, wante)
+    budget = _bf16_oracle_err(V.tiled_encode, sd, want, wante, tile_size=(32, 40), tile_stride=(24, 24), dim=dim)
+    print(f"vae tiled encode: ours {erre:.3e}  oracle-bf16 {budget:.3e}")
+    assert gote.shape == wante.shape and erre <= max(budget, 5e-3), (erre, budget)
+    # untiled public calls: decode clamps, encode of a batch of one
+    one = vae.decode(g["z"].to(torch.bfloat16), "cuda").float().cpu()
+    assert O.rel_l2(one, g["decode"].float().clamp(-1, 1)) < 2e-2
+
+
+def test_real_width_clip_against_oracle():
+    """dim 96 (the shipped Wan2.1 VAE width: 96/192/384 channels, two n-tiles, Cin % 64 != 0 k-blocks), a 9-frame
+    64 x 96 clip: encode and decode vs the fp32 oracle on this GPU; budget = the oracle's own bf16 run."""
+    from goal_force_b200.wan_vae import WanVideoVAEB200
+    sd = V.random_state_dict(dim=96, seed=5)
+    vae = WanVideoVAEB200(sd, dim=96)
+    g = torch.Generator().manual_seed(11)
+    z = torch.randn(1, 16, 3, 8, 12, generator=g)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        want = V.decode(sdc, z.cuda()).cpu()
+        got = vae._decode_clip(z[0].to(device="cuda", dtype=torch.bfloat16)).float().cpu().unsqueeze(0)
+        err = O.rel_l2(got, want)
+        budget = _bf16_oracle_err(V.decode, sd, z, want)
+        print(f"vae decode (dim 96): ours {err:.3e}  oracle-bf16 {budget:.3e}")
+        assert err <= max(budget, 4e-3), (err, budget)
+        video = want.clamp(-1, 1)
+        wante = V.encode(sdc, video.cuda()).cpu()
+        gote = vae._encode_clip(video[0].to(device="cuda", dtype=torch.bfloat16)).float().cpu().unsqueeze(0)
+        erre = O.rel_l2(gote, wante)
+        budget = _bf16_oracle_err(V.encode, sd, video, wante)
+        print(f"vae encode (dim 96): ours {erre:.3e}  oracle-bf16 {budget:.3e}")
+        assert erre <= max(budget, 4e-3), (erre, budget)
