@@ -33,6 +33,7 @@ SIGNATURES = {
     "gf_ctx_destroy": [_p],
     "gf_ctx_set_attention": [_p, _i, _i],
     "gf_ctx_set_gemm_raster": [_p, _i],
+    "gf_ctx_set_conv": [_p, _i],
     "gf_ctx_stats": [_p, ctypes.POINTER(_ll), ctypes.POINTER(_ll), ctypes.POINTER(_ll)],
     "gf_gemm_bf16": [_p, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p, _i, _p, _p, _ll, _i, _p],
     "gf_layernorm_bf16": [_p, _ll, _p, _ll, _i, _i, _f, _p, _p, _p, _p, _p],
@@ -125,6 +126,9 @@ def ctx() -> int:
         emu = int(os.environ.get("GF_ATTN_EMU_PAIRS", "-1"))
         if impl or emu >= 0:
             _check(load().gf_ctx_set_attention(c, impl, emu), "gf_ctx_set_attention")
+        ci = int(os.environ.get("GF_CONV_IMPL", "0"))
+        if ci:
+            _check(load().gf_ctx_set_conv(c, ci), "gf_ctx_set_conv")
         gm = int(os.environ.get("GF_GEMM_GROUP_M", "0"))
         if gm:
             _check(load().gf_ctx_set_gemm_raster(c, gm), "gf_ctx_set_gemm_raster")
@@ -312,6 +316,11 @@ def attention_tuning(impl: int = 0, emu_pairs: int = -1) -> None:
     """Select the attention kernel of this process's context (0 = per shape, 80 = decoupled 80-row blocks,
     128 = aliased 128-row blocks) and the share of exponentials evaluated on the FMA pipe (-1 = kernel default)."""
     _check(load().gf_ctx_set_attention(ctx(), impl, emu_pairs), "gf_ctx_set_attention")
+
+
+def conv_tuning(impl: int = 0) -> None:
+    """Convolution kernel choice of this process's context: impl 0 = per shape, 1 = always tap-by-tap."""
+    _check(load().gf_ctx_set_conv(ctx(), impl), "gf_ctx_set_conv")
 
 
 def gemm_tuning(group_m: int = 0) -> None:
@@ -543,7 +552,8 @@ def conv3d_cl(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, *, ke
     for nme, t in (("bias", bias), ("residual", residual), ("gamma", gamma), ("out", out), ("norm_out", norm_out)):
         if t is not None:
             _req(t, nme)
-    _call("conv3d", 2.0 * To * Ho * Wo * Cout * kt * kh * kw * Cin, load().gf_conv3d_cl_bf16, ctx(), x.data_ptr(), ldx, T,
+    _call(f"conv3d:{Cin}>{Cout}:k{kt}{kh}{kw}s{stride[0]}{stride[1]}", 2.0 * To * Ho * Wo * Cout * kt * kh * kw * Cin,
+          load().gf_conv3d_cl_bf16, ctx(), x.data_ptr(), ldx, T,
           H, W, Cin, w.data_ptr(), Cout, kt, kh, kw, stride[0], stride[1], stride[2], pad[0], pad[1], pad[2], _ptr(bias),
           _ptr(out), ldy, To, Ho, Wo, _ptr(residual), residual.stride(2) if residual is not None else 0,
           _ptr(norm_out), norm_out.stride(2) if norm_out is not None else 0, _ptr(gamma), 1 if silu else 0,

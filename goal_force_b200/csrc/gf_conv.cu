@@ -238,7 +238,7 @@ gf_conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
               }
               if (p.silu) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) y[j] = y[j] / (1.0f + __expf(-y[j]));
+                for (int j = 0; j < 8; ++j) y[j] = silu_fast(y[j]);
               }
               if (ok)
                 *reinterpret_cast<uint4*>(p.Y2 + pos * p.ldy2 + cg) =
@@ -264,6 +264,335 @@ gf_conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Halo form for 3x3 spatial windows with few output channels (Cout <= 128, stride 1).
+//
+// With N <= 128 the tap-by-tap form above is bound by operand traffic into the SM (about 56 B/clk/SM: 16 KB of A plus
+// N x 128 B of weights for 4 x 56 MMA cycles), not by the tensor core.  Here a CTA owns 32 x 8 output positions (two
+// 128-row accumulators) and, per (dt, 64-channel block), loads ONE 34 x 10 halo of the input (43.5 KB) instead of nine
+// shifted 128-row tiles: position (h, w) of the halo sits at row h*10 + w of a 128-byte-row, 128B-swizzled buffer, so
+// the A operand of tap (dh, dw) for accumulator `mh` is the same buffer read through a descriptor that starts at row
+// (mh*16 + dh)*10 + dw with a stride of 10 rows (1280 B) between 8-row groups -- the swizzle is a function of the
+// absolute shared-memory address for TMA and the tensor core alike (checked on B200: descriptors with the 'matrix base
+// offset' field set to (addr >> 7) & 7 give wrong results, plain start addresses are exact).  Each weight tile feeds both accumulators.
+// Operand bytes per MMA drop 3.3x (N = 96) and the kernel becomes tensor-bound.
+//
+// 320 threads: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter, one per accumulator).
+// The epilogue keeps the bf16 row in registers (Cout <= 128), frees the accumulator as soon as it has been read, and
+// moves R / Y / Y2 through a per-warp staging tile so that global accesses are 64-byte row segments.
+constexpr int HALO_THREADS = 320;
+constexpr int HALO_W = 8, HALO_H = 32;                   // output positions per CTA tile
+constexpr int HALO_ROWS = (HALO_W + 2) * (HALO_H + 2);   // 340
+constexpr int HALO_TX_BYTES = HALO_ROWS * 128;           // 43,520
+constexpr int HALO_STAGE_BYTES = 44 * 1024;
+constexpr int HALO_A_STAGES = 3;
+constexpr int HALO_MAX_B_STAGES = 8;
+constexpr int HALO_STG_PITCH = 80;                       // bytes per staged row: 32 bf16 + 16 B pad
+constexpr int HALO_STG_BYTES = 32 * HALO_STG_PITCH;      // per epilogue warp
+
+template <int NCH>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t b_base = smem_base + HALO_A_STAGES * HALO_STAGE_BYTES;
+  const uint32_t stg_base = b_base + p.stages * b_bytes;
+  const uint32_t bar_base = stg_base + 8 * HALO_STG_BYTES;
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto bfull_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (8 + HALO_MAX_B_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (8 + 2 * HALO_MAX_B_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (10 + 2 * HALO_MAX_B_STAGES + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (12 + 2 * HALO_MAX_B_STAGES);
+  auto smem_a = [&](int s) { return smem_base + s * HALO_STAGE_BYTES; };
+  auto smem_b = [&](int s) { return b_base + s * b_bytes; };
+
+  const int warp = threadIdx.x >> 5;
+  const int tiles_per_frame = p.nWt * p.nHt;
+  const int num_tiles = p.To * tiles_per_frame;
+  const int num_cb = (p.Cin + CONV_BK - 1) / CONV_BK;
+  const int kt = p.ntaps / 9;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < HALO_A_STAGES; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
+      for (int s = 0; s < p.stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<1>(tmem_ptr_smem, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (elect_one()) {
+      int as = 0; uint32_t aphase = 0;
+      int bs = 0; uint32_t bphase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tt = t / tiles_per_frame;
+        const int rem = t - tt * tiles_per_frame;
+        const int ht = rem / p.nWt, wt = rem - ht * p.nWt;
+        const int h0 = ht * HALO_H + p.tap_dh[0], w0 = wt * HALO_W + p.tap_dw[0];   // tap 0 is (dh, dw) = (-ph, -pw)
+        for (int dt = 0; dt < kt; ++dt) {
+          const int ct = tt * p.st + p.tap_dt[dt * 9];
+          for (int cb = 0; cb < num_cb; ++cb) {
+            mbar_wait(aempty_bar(as), aphase ^ 1u);
+            mbar_arrive_expect_tx(afull_bar(as), HALO_TX_BYTES);
+            tma_load_4d(smem_a(as), &maps.a[0], afull_bar(as), cb * CONV_BK, w0, h0, ct);
+            if (++as == HALO_A_STAGES) { as = 0; aphase ^= 1u; }
+            for (int sp = 0; sp < 9; ++sp) {
+              mbar_wait(bempty_bar(bs), bphase ^ 1u);
+              mbar_arrive_expect_tx(bfull_bar(bs), b_bytes);
+              tma_load_2d(smem_b(bs), &maps.b, bfull_bar(bs), (dt * 9 + sp) * p.Cin + cb * CONV_BK, 0);
+              if (++bs == p.stages) { bs = 0; bphase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    // The whole warp walks the loop (barrier waits and descriptor arithmetic stay warp-uniform, i.e. in uniform
+    // registers); one elected lane issues the MMAs and commits.  At N = 96 an MMA lasts 56 cycles, so the issue path
+    // per MMA has to stay well below that: taps and k-steps are fully unrolled, descriptors differ in their low word
+    // only (start address >> 4) and are built by adding constants.
+    {
+      const uint32_t idesc = idesc_bf16(CONV_BM, (uint32_t)p.BN, 0, 0);
+      constexpr uint64_t b_dbase = smem_desc_base(/*sbo=*/1024, /*lbo=*/16);
+      constexpr uint64_t a_dbase = smem_desc_base(/*sbo=*/(HALO_W + 2) * 128, /*lbo=*/16);
+      int as = 0; uint32_t aphase = 0;
+      int bs = 0; uint32_t bphase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        uint32_t accum = 0;
+        for (int dt = 0; dt < kt; ++dt) {
+          for (int cb = 0; cb < num_cb; ++cb) {
+            mbar_wait(afull_bar(as), aphase);
+            tc_fence_after();
+            const int kvalid = min(CONV_BK, p.Cin - cb * CONV_BK);
+            const int nk = (kvalid + 15) >> 4;
+            const uint64_t adesc0 = smem_desc(a_dbase, smem_a(as));
+#pragma unroll
+            for (int sp = 0; sp < 9; ++sp) {
+              constexpr int kRowUnits = 128 / 16;                 // one halo row in descriptor address units
+              const int tap_off = ((sp / 3) * (HALO_W + 2) + (sp % 3)) * kRowUnits;
+              mbar_wait(bfull_bar(bs), bphase);
+              tc_fence_after();
+              const uint64_t bdesc0 = smem_desc(b_dbase, smem_b(bs));
+              if (elect_one()) {
+#pragma unroll
+                for (int mh = 0; mh < 2; ++mh) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    if (k < nk)
+                      umma_ss<1>(d_tmem + mh * 128,
+                                 adesc0 + uint64_t(tap_off + mh * 16 * (HALO_W + 2) * kRowUnits + k * 2),
+                                 bdesc0 + uint64_t(k * 2), idesc, (k == 0) ? accum : 1u);
+                  }
+                }
+                tc_commit(bempty_bar(bs));
+              }
+              __syncwarp();
+              accum = 1u;
+              if (++bs == p.stages) { bs = 0; bphase ^= 1u; }
+            }
+            if (elect_one()) tc_commit(aempty_bar(as));
+            __syncwarp();
+            if (++as == HALO_A_STAGES) { as = 0; aphase ^= 1u; }
+          }
+        }
+        if (elect_one()) tc_commit(tfull_bar(acc));
+        __syncwarp();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..9)
+    const int ew = warp - 2;
+    const int mh = ew >> 2;                     // accumulator (upper / lower 16 tile rows)
+    const int q = warp & 3;                     // TMEM lane quarter
+    const int lane = (int)lane_id();
+    const long long frame = (long long)p.Ho * p.Wo;
+    uint8_t* stg = smem_raw + (stg_base - smem_u32(smem_raw)) + ew * HALO_STG_BYTES;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int tt = t / tiles_per_frame;
+      const int rem = t - tt * tiles_per_frame;
+      const int ht = rem / p.nWt, wt = rem - ht * p.nWt;
+      const int hbase = ht * HALO_H + mh * 16 + q * 4;       // tile row of this warp's row 0
+      const int w0 = wt * HALO_W;
+      // own row (TMEM lane) and the four rows this lane serves in the coalesced phase
+      const int h_own = hbase + (lane >> 3), w_own = w0 + (lane & 7);
+      const bool ok_own = h_own < p.Ho && w_own < p.Wo;
+      const long long pos_own = (long long)tt * frame + (long long)h_own * p.Wo + w_own;
+      long long pos_co[4];
+      bool ok_co[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = (lane >> 2) + 8 * i;
+        const int h = hbase + (row >> 3), w = w0 + (row & 7);
+        ok_co[i] = h < p.Ho && w < p.Wo;
+        pos_co[i] = (long long)tt * frame + (long long)h * p.Wo + w;
+      }
+      const int cv = lane & 3;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * 256 + mh * 128;
+      uint32_t xs[NCH * 16];
+      float ss = 0.0f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col0 = c * 32;
+        if (col0 < p.cout_store) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          uint32_t rw[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rw[j] = 0u;
+          if (p.R) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 r4 = make_uint4(0, 0, 0, 0);
+              if (ok_co[i] && col0 + cv * 8 < p.cout_store)
+                r4 = *reinterpret_cast<const uint4*>(p.R + pos_co[i] * p.ldr + col0 + cv * 8);
+              *reinterpret_cast<uint4*>(stg + ((lane >> 2) + 8 * i) * HALO_STG_PITCH + cv * 16) = r4;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 r4 = *reinterpret_cast<const uint4*>(stg + lane * HALO_STG_PITCH + g * 16);
+              rw[g * 4] = r4.x; rw[g * 4 + 1] = r4.y; rw[g * 4 + 2] = r4.z; rw[g * 4 + 3] = r4.w;
+            }
+            __syncwarp();
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int cg = col0 + g * 8;
+            uint4 bv = make_uint4(0, 0, 0, 0);
+            if (p.bias && cg < p.cout_store) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + cg));
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // bf16(acc + bias), then the packed bf16 add of the residual (one rounding each, as the torch ops);
+              // channels in [Cout, cout_store) are exact zeros (zero-filled weights, zero bias / residual padding)
+              uint32_t xp = pack_bf16x2(__uint_as_float(v[g * 8 + 2 * j]) + bf16_lo(bw[j]),
+                                        __uint_as_float(v[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
+              if (p.R) xp = hadd2_bf16(xp, rw[g * 4 + j]);
+              ss = fmaf(bf16_lo(xp), bf16_lo(xp), ss);
+              ss = fmaf(bf16_hi(xp), bf16_hi(xp), ss);
+              xs[c * 16 + g * 4 + j] = xp;
+            }
+          }
+          if (p.Y) {
+            if (p.ncthw) {
+              if (ok_own) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int ch = col0 + 2 * j;
+                  if (ch < p.Cout)
+                    p.Y[(long long)ch * p.To * frame + pos_own] =
+                        __ushort_as_bfloat16((unsigned short)(xs[c * 16 + j] & 0xFFFFu));
+                  if (ch + 1 < p.Cout)
+                    p.Y[(long long)(ch + 1) * p.To * frame + pos_own] =
+                        __ushort_as_bfloat16((unsigned short)(xs[c * 16 + j] >> 16));
+                }
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                *reinterpret_cast<uint4*>(stg + lane * HALO_STG_PITCH + g * 16) =
+                    make_uint4(xs[c * 16 + g * 4], xs[c * 16 + g * 4 + 1], xs[c * 16 + g * 4 + 2],
+                               xs[c * 16 + g * 4 + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (ok_co[i] && col0 + cv * 8 < p.cout_store)
+                  *reinterpret_cast<uint4*>(p.Y + pos_co[i] * p.ldy + col0 + cv * 8) =
+                      *reinterpret_cast<const uint4*>(stg + ((lane >> 2) + 8 * i) * HALO_STG_PITCH + cv * 16);
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+      // accumulator fully read: hand it back before the second (register-only) pass
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (p.Y2) {
+        const float rinv = sqrtf((float)p.Cout) / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int col0 = c * 32;
+          if (col0 < p.cout_store) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int cg = col0 + g * 8;
+              uint4 gv = make_uint4(0, 0, 0, 0);
+              if (cg < p.cout_store) gv = __ldg(reinterpret_cast<const uint4*>(p.gamma + cg));
+              const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float y0 = bf16_lo(xs[c * 16 + g * 4 + j]) * rinv * bf16_lo(gw[j]);
+                float y1 = bf16_hi(xs[c * 16 + g * 4 + j]) * rinv * bf16_hi(gw[j]);
+                if (p.silu) {
+                  y0 = silu_fast(y0);
+                  y1 = silu_fast(y1);
+                }
+                o[j] = pack_bf16x2(y0, y1);
+              }
+              *reinterpret_cast<uint4*>(stg + lane * HALO_STG_PITCH + g * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (ok_co[i] && col0 + cv * 8 < p.cout_store)
+                *reinterpret_cast<uint4*>(p.Y2 + pos_co[i] * p.ldy2 + col0 + cv * 8) =
+                    *reinterpret_cast<const uint4*>(stg + ((lane >> 2) + 8 * i) * HALO_STG_PITCH + cv * 16);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+template <int NCH>
+static int launch_halo(const ConvMaps& maps, const ConvParams& p, int smem, int grid, cudaStream_t s) {
+  auto kern = gf_conv3d_halo_kernel<NCH>;
+  static bool configured[64] = {};
+  if (int e = gf_set_smem_once(configured, reinterpret_cast<const void*>(kern), 227 * 1024)) return e;
+  kern<<<grid, HALO_THREADS, smem, s>>>(maps, p);
+  return (int)cudaGetLastError();
+}
+
 static inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 }  // namespace gf
@@ -274,7 +603,6 @@ extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int 
                                  long long ldr, void* Y2, long long ldy2, const void* gamma, int silu, int out_ncthw,
                                  void* stream) {
   using namespace gf;
-  (void)ctx;
   if (!X || !Wt || (!Y && !Y2) || T <= 0 || H <= 0 || W <= 0 || To <= 0 || Ho <= 0 || Wo <= 0) return GF_ERR_BAD_ARG;
   if (Cin <= 0 || (Cin % 8) || (ldx % 8) || ldx < Cin || Cout <= 0) return GF_ERR_BAD_ARG;
   if (kt < 1 || kh < 1 || kw < 1 || kt * kh * kw > CONV_MAX_TAPS) return GF_ERR_UNSUPPORTED;
@@ -332,6 +660,42 @@ extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int 
         p.tap_dh[tap] = (signed char)oh;
         p.tap_dw[tap] = (signed char)ow;
       }
+
+  const CtxTuning tune = gf_ctx_tuning(ctx);
+  const bool halo = kh == 3 && kw == 3 && sh == 1 && st == 1 && cout32 <= 128 && tune.conv_impl != 1;
+  if (halo) {
+    // 32 x 8 output positions per CTA, one 34 x 10 input halo per (dt, channel block); see gf_conv3d_halo_kernel
+    p.num_n_tiles = 1;
+    p.BN = cout32;
+    p.bw_shift = 3;
+    p.nWt = (Wo + HALO_W - 1) / HALO_W;
+    p.nHt = (Ho + HALO_H - 1) / HALO_H;
+    const int fixed = HALO_A_STAGES * HALO_STAGE_BYTES + 8 * HALO_STG_BYTES + 1024 + 512;
+    p.stages = (224 * 1024 - fixed) / (p.BN * 128);
+    if (p.stages > HALO_MAX_B_STAGES) p.stages = HALO_MAX_B_STAGES;
+    ConvMaps hm;
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)T};
+    const uint64_t strides[3] = {(uint64_t)ldx * 2, (uint64_t)ldx * 2 * W, (uint64_t)ldx * 2 * W * H};
+    const uint32_t box[4] = {(uint32_t)CONV_BK, (uint32_t)(HALO_W + 2), (uint32_t)(HALO_H + 2), 1u};
+    int hrc = gf_make_tmap_4d_bf16(&hm.a[0], X, dims, strides, box);
+    if (hrc) return hrc;
+    for (int i = 1; i < 4; ++i) hm.a[i] = hm.a[0];
+    hrc = gf_make_tmap_2d_bf16(&hm.b, Wt, (uint64_t)p.ntaps * Cin, (uint64_t)Cout, (uint64_t)p.ntaps * Cin, CONV_BK,
+                               (uint32_t)p.BN);
+    if (hrc) return hrc;
+    const int hsmem = fixed + p.stages * p.BN * 128;
+    const long long htiles = (long long)To * p.nWt * p.nHt;
+    int hgrid = gf_num_sms();
+    if (hgrid <= 0) return GF_ERR_NO_DRIVER;
+    if (hgrid > htiles) hgrid = (int)htiles;
+    cudaStream_t hs = reinterpret_cast<cudaStream_t>(stream);
+    switch (p.BN / 32) {
+      case 1: return launch_halo<1>(hm, p, hsmem, hgrid, hs);
+      case 2: return launch_halo<2>(hm, p, hsmem, hgrid, hs);
+      case 3: return launch_halo<3>(hm, p, hsmem, hgrid, hs);
+      default: return launch_halo<4>(hm, p, hsmem, hgrid, hs);
+    }
+  }
 
   ConvMaps maps;
   const char* xb = reinterpret_cast<const char*>(X);

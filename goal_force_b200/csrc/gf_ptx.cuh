@@ -370,4 +370,16 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return y;
 }
 
+// silu(x) = x * sigmoid(x) = h * tanh(h) + h with h = x / 2: one MUFU, no division (the IEEE division's slow path is
+// taken whenever 1 + exp(-x) overflows).  tanh.approx is good to ~2^-11, far below the bf16 rounding of the result.
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
+// packed bf16 add with one rounding per lane (== torch's bf16 add)
+__device__ __forceinline__ uint32_t hadd2_bf16(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hadd2_rn(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
 }  // namespace gf

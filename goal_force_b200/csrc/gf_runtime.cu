@@ -156,6 +156,12 @@ extern "C" int gf_ctx_set_gemm_raster(gf_ctx* ctx, int group_m) {
   return 0;
 }
 
+extern "C" int gf_ctx_set_conv(gf_ctx* ctx, int impl) {
+  if (!ctx || impl < 0 || impl > 1) return GF_ERR_BAD_ARG;
+  ctx->tuning.conv_impl = impl;
+  return 0;
+}
+
 extern "C" int gf_ctx_stats(gf_ctx* ctx, long long* tmap_entries, long long* tmap_hits, long long* tmap_misses) {
   if (!ctx) return GF_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lock(ctx->mu);

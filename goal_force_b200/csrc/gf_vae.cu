@@ -61,8 +61,8 @@ __global__ void vae_rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long lon
           float a = bf16_lo(w[j]) * rinv * bf16_lo(gw[j]);
           float b = bf16_hi(w[j]) * rinv * bf16_hi(gw[j]);
           if (silu) {
-            a = a / (1.0f + __expf(-a));
-            b = b / (1.0f + __expf(-b));
+            a = silu_fast(a);
+            b = silu_fast(b);
           }
           o[j] = pack_bf16x2(a, b);
         }

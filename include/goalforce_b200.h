@@ -46,12 +46,15 @@ int gf_abi_version(void);
  * sequences the 80-row decoupled kernel, as a CTA pair when the 512-row work items fill the SM pairs; the 128-row
  * kernel for Lk <= 1024), 80 / 160 / 128 = forced (160 = CTA-pair form of 80); emu_pairs -1 = kernel default, or
  * 0/2/4/6 column pairs per 16 whose exp2 runs on the FMA pipe.  gf_ctx_set_gemm_raster: rasterisation group height in
- * m-tiles, 0 = per-shape choice.  gf_ctx_stats: descriptor-cache counters (any pointer may be NULL). */
+ * m-tiles, 0 = per-shape choice.  gf_ctx_set_conv: impl 0 = per-shape choice of the convolution kernel (halo form for
+ * 3x3 windows with Cout <= 128), 1 = always the tap-by-tap form.
+ * gf_ctx_stats: descriptor-cache counters (any pointer may be NULL). */
 typedef struct gf_ctx gf_ctx;
 int gf_ctx_create(gf_ctx** ctx);
 int gf_ctx_destroy(gf_ctx* ctx);
 int gf_ctx_set_attention(gf_ctx* ctx, int impl, int emu_pairs);
 int gf_ctx_set_gemm_raster(gf_ctx* ctx, int group_m);
+int gf_ctx_set_conv(gf_ctx* ctx, int impl);
 int gf_ctx_stats(gf_ctx* ctx, long long* tmap_entries, long long* tmap_hits, long long* tmap_misses);
 
 /* Number of SMs of the current CUDA device (148 on B200); <= 0 if no device. */

@@ -84,13 +84,15 @@ def main():
     single_enc = section("ours_single_encode", lambda: vae.encode(video, "cuda", tiled=False))
     try:
         res["ours_single_decode_kernels"] = conv_flops(vae, lambda: vae.decode(z, "cuda", tiled=False))
-        k = res["ours_single_decode_kernels"]
-        if "conv3d" in k:
-            k["conv3d"]["tflops"] = round(k["conv3d"]["work"] / k["conv3d"]["ms"] / 1e9, 1)
         res["ours_single_encode_kernels"] = conv_flops(vae, lambda: vae.encode(video, "cuda", tiled=False))
-        k = res["ours_single_encode_kernels"]
-        if "conv3d" in k:
-            k["conv3d"]["tflops"] = round(k["conv3d"]["work"] / k["conv3d"]["ms"] / 1e9, 1)
+        for key in ("ours_single_decode_kernels", "ours_single_encode_kernels"):
+            tot_ms = tot_work = 0.0
+            for tag, k in res[key].items():
+                if tag.startswith("conv3d"):
+                    k["tflops"] = round(k["work"] / k["ms"] / 1e9, 1)
+                    tot_ms += k["ms"]
+                    tot_work += k["work"]
+            res[key]["conv3d_total"] = {"ms": round(tot_ms, 2), "tflops": round(tot_work / tot_ms / 1e9, 1)}
     except Exception as e:  # noqa: BLE001
         res["kernels_error"] = repr(e)[:300]
     dump()
