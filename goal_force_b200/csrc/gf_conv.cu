@@ -20,6 +20,7 @@
 //   Y  = v                                     (channels-last, or (C, T, H, W) for the 3-channel head)
 //   Y2 = silu(v / max(|v|_2, 1e-12) * sqrt(C) * gamma)   (the NEXT layer's RMS_norm + SiLU, :55-70,283-288) when the
 //        whole channel row lives in one tile (Cout <= 256); two passes over the accumulator in TMEM.
+#include <type_traits>
 #include "gf_ptx.cuh"
 #include "gf_api_internal.h"
 
@@ -32,6 +33,8 @@ constexpr int CONV_MAX_TAPS = 27;
 constexpr int CONV_MAX_STAGES = 8;
 constexpr int CONV_A_BYTES = CONV_BM * CONV_BK * 2;   // 16 KB
 constexpr int CONV_SMEM_BUDGET = 200 * 1024;
+constexpr int CONV_STG_PITCH = 80;                       // epilogue staging: bytes per row (32 bf16 + 16 B pad)
+constexpr int CONV_STG_BYTES = 32 * CONV_STG_PITCH;      // per epilogue warp
 
 struct ConvMaps {
   CUtensorMap a[4];   // input clip, one map per (h, w) parity of a strided convolution
@@ -59,12 +62,144 @@ struct ConvParams {
   const __nv_bfloat16* gamma;
 };
 
+// ------------------------------------------------------------------------------------------------------------------
+// Epilogue of one warp for its 32 accumulator rows (TMEM lanes) and up to NCH x 32 columns starting at column n0.
+// Pass 0 reads the accumulator, adds bias and residual (bf16 roundings of the torch ops), keeps the packed bf16 row in
+// registers, stores Y and hands the accumulator back; pass 1 (fused RMS_norm + SiLU of the next layer) works from the
+// registers.  R / Y / Y2 move through the warp's staging tile `stg` (32 rows x 80 B) so that every global access is a
+// 64-byte row segment: lane l owns row l in the math, and serves rows (l >> 2) + 8 i, 16-byte column (l & 3) in the I/O.
+template <int NCH>
+__device__ __forceinline__ void conv_epilogue_rows(const ConvParams& p, uint32_t t_addr, int n0, uint8_t* stg, int lane,
+                                                   long long frame, long long pos_own, bool ok_own,
+                                                   const long long (&pos_co)[4], const bool (&ok_co)[4],
+                                                   uint32_t tempty_addr) {
+  const int cv = lane & 3;
+  uint32_t xs[NCH * 16];
+  float ss = 0.0f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col0 = n0 + c * 32;
+    if (c * 32 < p.BN && col0 < p.cout_store) {
+      uint32_t v[32];
+      tmem_ld32(t_addr + c * 32, v);
+      uint32_t rw[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) rw[j] = 0u;
+      if (p.R) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 r4 = make_uint4(0, 0, 0, 0);
+          if (ok_co[i] && col0 + cv * 8 < p.cout_store)
+            r4 = *reinterpret_cast<const uint4*>(p.R + pos_co[i] * p.ldr + col0 + cv * 8);
+          *reinterpret_cast<uint4*>(stg + ((lane >> 2) + 8 * i) * CONV_STG_PITCH + cv * 16) = r4;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 r4 = *reinterpret_cast<const uint4*>(stg + lane * CONV_STG_PITCH + g * 16);
+          rw[g * 4] = r4.x; rw[g * 4 + 1] = r4.y; rw[g * 4 + 2] = r4.z; rw[g * 4 + 3] = r4.w;
+        }
+        __syncwarp();
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int cg = col0 + g * 8;
+        uint4 bv = make_uint4(0, 0, 0, 0);
+        if (p.bias && cg < p.cout_store) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + cg));
+        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // bf16(acc + bias), then the packed bf16 add of the residual (one rounding each, as the torch ops);
+          // channels in [Cout, cout_store) are exact zeros (zero-filled weights, zero bias / residual padding)
+          uint32_t xp = pack_bf16x2(__uint_as_float(v[g * 8 + 2 * j]) + bf16_lo(bw[j]),
+                                    __uint_as_float(v[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
+          xp = hadd2_bf16(xp, rw[g * 4 + j]);        // rw == 0 without a residual: x + 0 is exact
+          ss = fmaf(bf16_lo(xp), bf16_lo(xp), ss);
+          ss = fmaf(bf16_hi(xp), bf16_hi(xp), ss);
+          xs[c * 16 + g * 4 + j] = xp;
+        }
+      }
+      if (p.Y) {
+        if (p.ncthw) {
+          if (c == 0 && ok_own) {       // (C, T, H, W) output: Cout <= 32 (checked on the host)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int ch = col0 + 2 * j;
+              if (ch < p.Cout)
+                p.Y[(long long)ch * p.To * frame + pos_own] =
+                    __ushort_as_bfloat16((unsigned short)(xs[c * 16 + j] & 0xFFFFu));
+              if (ch + 1 < p.Cout)
+                p.Y[(long long)(ch + 1) * p.To * frame + pos_own] =
+                    __ushort_as_bfloat16((unsigned short)(xs[c * 16 + j] >> 16));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(stg + lane * CONV_STG_PITCH + g * 16) =
+                make_uint4(xs[c * 16 + g * 4], xs[c * 16 + g * 4 + 1], xs[c * 16 + g * 4 + 2],
+                           xs[c * 16 + g * 4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (ok_co[i] && col0 + cv * 8 < p.cout_store)
+              *reinterpret_cast<uint4*>(p.Y + pos_co[i] * p.ldy + col0 + cv * 8) =
+                  *reinterpret_cast<const uint4*>(stg + ((lane >> 2) + 8 * i) * CONV_STG_PITCH + cv * 16);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  // accumulator fully read: hand it back before the second (register-only) pass
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tempty_addr);
+  if (p.Y2) {
+    const float rinv = sqrtf((float)p.Cout) / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col0 = n0 + c * 32;
+      if (c * 32 < p.BN && col0 < p.cout_store) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int cg = col0 + g * 8;
+          uint4 gv = make_uint4(0, 0, 0, 0);
+          if (cg < p.cout_store) gv = __ldg(reinterpret_cast<const uint4*>(p.gamma + cg));
+          const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float y0 = bf16_lo(xs[c * 16 + g * 4 + j]) * rinv * bf16_lo(gw[j]);
+            float y1 = bf16_hi(xs[c * 16 + g * 4 + j]) * rinv * bf16_hi(gw[j]);
+            // silu(y) = h tanh(h) + h, h = y / 2; without SiLU the tanh factor is replaced by 1 (h + h = y exactly)
+            const float h0 = 0.5f * y0, h1 = 0.5f * y1;
+            o[j] = pack_bf16x2(fmaf(h0, p.silu ? tanh_approx(h0) : 1.0f, h0), fmaf(h1, p.silu ? tanh_approx(h1) : 1.0f, h1));
+          }
+          *reinterpret_cast<uint4*>(stg + lane * CONV_STG_PITCH + g * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (ok_co[i] && col0 + cv * 8 < p.cout_store)
+            *reinterpret_cast<uint4*>(p.Y2 + pos_co[i] * p.ldy2 + col0 + cv * 8) =
+                *reinterpret_cast<const uint4*>(stg + ((lane >> 2) + 8 * i) * CONV_STG_PITCH + cv * 16);
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+template <int NCH>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 gf_conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = CONV_A_BYTES + (uint32_t)p.BN * 128u;
-  const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+  const uint32_t stg_base = smem_base + p.stages * stage_bytes;
+  const uint32_t bar_base = stg_base + 4 * CONV_STG_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (CONV_MAX_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * CONV_MAX_STAGES + a); };
@@ -130,8 +265,8 @@ gf_conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (elect_one()) {
+    // ===================================================== MMA issuer (whole warp walks the loop, one lane issues)
+    {
       const uint32_t idesc = idesc_bf16(CONV_BM, (uint32_t)p.BN, 0, 0);
       constexpr uint64_t dbase = smem_desc_base(/*sbo=*/1024, /*lbo=*/16);
       int stage = 0; uint32_t phase = 0;
@@ -140,23 +275,29 @@ gf_conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        uint32_t first = 0;
+        uint32_t accum = 0;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           for (int cb = 0; cb < num_cb; ++cb) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint32_t a_addr = smem_a(stage), b_addr = smem_b(stage);
+            const uint64_t adesc0 = smem_desc(dbase, smem_a(stage)), bdesc0 = smem_desc(dbase, smem_b(stage));
             const int kvalid = min(CONV_BK, p.Cin - cb * CONV_BK);
             const int nk = (kvalid + 15) >> 4;
-            for (int k = 0; k < nk; ++k) {
-              umma_ss<1>(d_tmem, smem_desc(dbase, a_addr + k * 32), smem_desc(dbase, b_addr + k * 32), idesc, first);
-              first = 1u;
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < nk)
+                  umma_ss<1>(d_tmem, adesc0 + uint64_t(k * 2), bdesc0 + uint64_t(k * 2), idesc, (k == 0) ? accum : 1u);
+              }
+              tc_commit(empty_bar(stage));
             }
-            tc_commit(empty_bar(stage));
+            __syncwarp();
+            accum = 1u;
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
-        tc_commit(tfull_bar(acc));
+        if (elect_one()) tc_commit(tfull_bar(acc));
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -164,94 +305,31 @@ gf_conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     // ===================================================== epilogue (warps 2..5)
     const int q = warp & 3;
     const int lane = (int)lane_id();
-    const int r = q * 32 + lane;
-    const int hh = r >> p.bw_shift, ww = r & (BW - 1);
     const long long frame = (long long)p.Ho * p.Wo;
-    const bool fused_norm = p.Y2 != nullptr;
+    uint8_t* stg = smem_raw + (stg_base - smem_u32(smem_raw)) + (warp - 2) * CONV_STG_BYTES;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
       const int tt = mt / tiles_per_frame;
       const int rem = mt - tt * tiles_per_frame;
       const int ht = rem / p.nWt, wt = rem - ht * p.nWt;
-      const int h = ht * BH + hh, w = wt * BW + ww, n0 = nt * p.BN;
-      const bool ok = h < p.Ho && w < p.Wo;
-      const long long pos = (long long)tt * frame + (long long)h * p.Wo + w;
+      const int r_own = q * 32 + lane;
+      const int h_own = ht * BH + (r_own >> p.bw_shift), w_own = wt * BW + (r_own & (BW - 1));
+      const bool ok_own = h_own < p.Ho && w_own < p.Wo;
+      const long long pos_own = (long long)tt * frame + (long long)h_own * p.Wo + w_own;
+      long long pos_co[4];
+      bool ok_co[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = q * 32 + (lane >> 2) + 8 * i;
+        const int h = ht * BH + (r >> p.bw_shift), w = wt * BW + (r & (BW - 1));
+        ok_co[i] = h < p.Ho && w < p.Wo;
+        pos_co[i] = (long long)tt * frame + (long long)h * p.Wo + w;
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * 256;
-      float ss = 0.0f;
-      float rinv = 0.0f;
-      const int passes = fused_norm ? 2 : 1;
-      for (int pass = 0; pass < passes; ++pass) {
-#pragma unroll 1
-        for (int c = 0; c < p.BN / 32; ++c) {
-          const int col0 = n0 + c * 32;
-          if (col0 >= p.cout_store) break;                 // uniform over the CTA
-          uint32_t v[32];
-          tmem_ld32(t_addr + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int cg = col0 + g * 8;
-            if (cg >= p.cout_store) break;
-            uint4 bv = make_uint4(0, 0, 0, 0), rv = make_uint4(0, 0, 0, 0);
-            if (p.bias) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + cg));
-            if (p.R && ok) rv = *reinterpret_cast<const uint4*>(p.R + pos * p.ldr + cg);
-            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-            float x[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              x[2 * j] = round_bf16(__uint_as_float(v[g * 8 + 2 * j]) + bf16_lo(bw[j]));
-              x[2 * j + 1] = round_bf16(__uint_as_float(v[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
-              if (p.R) {
-                x[2 * j] = round_bf16(x[2 * j] + bf16_lo(rw[j]));
-                x[2 * j + 1] = round_bf16(x[2 * j + 1] + bf16_hi(rw[j]));
-              }
-            }
-            if (pass == 0) {
-              if (fused_norm) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (cg + j < p.Cout) ss += x[j] * x[j];
-              }
-              if (p.Y && ok) {
-                if (p.ncthw) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    if (cg + j < p.Cout) p.Y[(long long)(cg + j) * p.To * frame + pos] = __float2bfloat16_rn(x[j]);
-                } else {
-                  *reinterpret_cast<uint4*>(p.Y + pos * p.ldy + cg) =
-                      make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                                 pack_bf16x2(x[6], x[7]));
-                }
-              }
-            } else {
-              const uint4 gv = __ldg(reinterpret_cast<const uint4*>(p.gamma + cg));
-              const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-              float y[8];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                y[2 * j] = x[2 * j] * rinv * bf16_lo(gw[j]);
-                y[2 * j + 1] = x[2 * j + 1] * rinv * bf16_hi(gw[j]);
-              }
-              if (p.silu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) y[j] = silu_fast(y[j]);
-              }
-              if (ok)
-                *reinterpret_cast<uint4*>(p.Y2 + pos * p.ldy2 + cg) =
-                    make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
-                               pack_bf16x2(y[6], y[7]));
-            }
-          }
-        }
-        if (pass == 0 && fused_norm) rinv = sqrtf((float)p.Cout) / fmaxf(sqrtf(ss), 1e-12f);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      conv_epilogue_rows<NCH>(p, t_addr, nt * p.BN, stg, lane, frame, pos_own, ok_own, pos_co, ok_co, tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -285,20 +363,19 @@ constexpr int HALO_W = 8, HALO_H = 32;                   // output positions per
 constexpr int HALO_ROWS = (HALO_W + 2) * (HALO_H + 2);   // 340
 constexpr int HALO_TX_BYTES = HALO_ROWS * 128;           // 43,520
 constexpr int HALO_STAGE_BYTES = 44 * 1024;
-constexpr int HALO_A_STAGES = 3;
-constexpr int HALO_MAX_B_STAGES = 8;
-constexpr int HALO_STG_PITCH = 80;                       // bytes per staged row: 32 bf16 + 16 B pad
-constexpr int HALO_STG_BYTES = 32 * HALO_STG_PITCH;      // per epilogue warp
+constexpr int HALO_A_STAGES = 2;
+constexpr int HALO_MAX_B_STAGES = 4;
 
 template <int NCH>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t b_tap_bytes = (uint32_t)p.BN * 128u;      // weights of one tap: BN rows x 64 channels
+  const uint32_t b_bytes = 3u * b_tap_bytes;               // a B stage holds one window row (dw = 0, 1, 2)
   const uint32_t b_base = smem_base + HALO_A_STAGES * HALO_STAGE_BYTES;
   const uint32_t stg_base = b_base + p.stages * b_bytes;
-  const uint32_t bar_base = stg_base + 8 * HALO_STG_BYTES;
+  const uint32_t bar_base = stg_base + 8 * CONV_STG_BYTES;
   auto afull_bar = [&](int s) { return bar_base + 8u * s; };
   auto aempty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
   auto bfull_bar = [&](int s) { return bar_base + 8u * (8 + s); };
@@ -353,10 +430,13 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
             mbar_arrive_expect_tx(afull_bar(as), HALO_TX_BYTES);
             tma_load_4d(smem_a(as), &maps.a[0], afull_bar(as), cb * CONV_BK, w0, h0, ct);
             if (++as == HALO_A_STAGES) { as = 0; aphase ^= 1u; }
-            for (int sp = 0; sp < 9; ++sp) {
+            for (int dh = 0; dh < 3; ++dh) {
               mbar_wait(bempty_bar(bs), bphase ^ 1u);
               mbar_arrive_expect_tx(bfull_bar(bs), b_bytes);
-              tma_load_2d(smem_b(bs), &maps.b, bfull_bar(bs), (dt * 9 + sp) * p.Cin + cb * CONV_BK, 0);
+#pragma unroll
+              for (int dw = 0; dw < 3; ++dw)
+                tma_load_2d(smem_b(bs) + dw * b_tap_bytes, &maps.b, bfull_bar(bs),
+                            (dt * 9 + dh * 3 + dw) * p.Cin + cb * CONV_BK, 0);
               if (++bs == p.stages) { bs = 0; bphase ^= 1u; }
             }
           }
@@ -387,24 +467,37 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
             tc_fence_after();
             const int kvalid = min(CONV_BK, p.Cin - cb * CONV_BK);
             const int nk = (kvalid + 15) >> 4;
-            const uint64_t adesc0 = smem_desc(a_dbase, smem_a(as));
-#pragma unroll
-            for (int sp = 0; sp < 9; ++sp) {
-              constexpr int kRowUnits = 128 / 16;                 // one halo row in descriptor address units
-              const int tap_off = ((sp / 3) * (HALO_W + 2) + (sp % 3)) * kRowUnits;
+            const uint32_t a_lo0 = (uint32_t)smem_desc(a_dbase, smem_a(as));
+            constexpr uint32_t a_hi = (uint32_t)(a_dbase >> 32), b_hi = (uint32_t)(b_dbase >> 32);
+            constexpr int kRowUnits = 128 / 16;                      // one halo row in descriptor address units
+            constexpr int kHalf = 16 * (HALO_W + 2) * kRowUnits;     // second accumulator: 16 tile rows further down
+#pragma unroll 1
+            for (int dh = 0; dh < 3; ++dh) {
               mbar_wait(bfull_bar(bs), bphase);
               tc_fence_after();
-              const uint64_t bdesc0 = smem_desc(b_dbase, smem_b(bs));
+              const uint32_t b_lo = (uint32_t)smem_desc(b_dbase, smem_b(bs));
+              const uint32_t a_lo = a_lo0 + (uint32_t)(dh * (HALO_W + 2) * kRowUnits);
+              const uint32_t b_tap_units = b_tap_bytes >> 4;
               if (elect_one()) {
+                // one window row: 3 taps x 2 accumulators x nk k-steps, straight-line for every nk
+                auto issue = [&](auto nk_c) {
+                  constexpr int NK = decltype(nk_c)::value;
 #pragma unroll
-                for (int mh = 0; mh < 2; ++mh) {
+                  for (int dw = 0; dw < 3; ++dw) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    if (k < nk)
-                      umma_ss<1>(d_tmem + mh * 128,
-                                 adesc0 + uint64_t(tap_off + mh * 16 * (HALO_W + 2) * kRowUnits + k * 2),
-                                 bdesc0 + uint64_t(k * 2), idesc, (k == 0) ? accum : 1u);
+                    for (int mh = 0; mh < 2; ++mh) {
+#pragma unroll
+                      for (int k = 0; k < NK; ++k)
+                        umma_ss_lohi(d_tmem + mh * 128, a_lo + dw * kRowUnits + mh * kHalf + k * 2, a_hi,
+                                     b_lo + dw * b_tap_units + k * 2, b_hi, idesc, (dw == 0 && k == 0) ? accum : 1u);
+                    }
                   }
+                };
+                switch (nk) {
+                  case 4: issue(std::integral_constant<int, 4>{}); break;
+                  case 3: issue(std::integral_constant<int, 3>{}); break;
+                  case 2: issue(std::integral_constant<int, 2>{}); break;
+                  default: issue(std::integral_constant<int, 1>{}); break;
                 }
                 tc_commit(bempty_bar(bs));
               }
@@ -429,7 +522,7 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     const int q = warp & 3;                     // TMEM lane quarter
     const int lane = (int)lane_id();
     const long long frame = (long long)p.Ho * p.Wo;
-    uint8_t* stg = smem_raw + (stg_base - smem_u32(smem_raw)) + ew * HALO_STG_BYTES;
+    uint8_t* stg = smem_raw + (stg_base - smem_u32(smem_raw)) + ew * CONV_STG_BYTES;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int tt = t / tiles_per_frame;
@@ -450,129 +543,11 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
         ok_co[i] = h < p.Ho && w < p.Wo;
         pos_co[i] = (long long)tt * frame + (long long)h * p.Wo + w;
       }
-      const int cv = lane & 3;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * 256 + mh * 128;
-      uint32_t xs[NCH * 16];
-      float ss = 0.0f;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int col0 = c * 32;
-        if (col0 < p.cout_store) {
-          uint32_t v[32];
-          tmem_ld32(t_addr + c * 32, v);
-          uint32_t rw[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) rw[j] = 0u;
-          if (p.R) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 r4 = make_uint4(0, 0, 0, 0);
-              if (ok_co[i] && col0 + cv * 8 < p.cout_store)
-                r4 = *reinterpret_cast<const uint4*>(p.R + pos_co[i] * p.ldr + col0 + cv * 8);
-              *reinterpret_cast<uint4*>(stg + ((lane >> 2) + 8 * i) * HALO_STG_PITCH + cv * 16) = r4;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint4 r4 = *reinterpret_cast<const uint4*>(stg + lane * HALO_STG_PITCH + g * 16);
-              rw[g * 4] = r4.x; rw[g * 4 + 1] = r4.y; rw[g * 4 + 2] = r4.z; rw[g * 4 + 3] = r4.w;
-            }
-            __syncwarp();
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int cg = col0 + g * 8;
-            uint4 bv = make_uint4(0, 0, 0, 0);
-            if (p.bias && cg < p.cout_store) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + cg));
-            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              // bf16(acc + bias), then the packed bf16 add of the residual (one rounding each, as the torch ops);
-              // channels in [Cout, cout_store) are exact zeros (zero-filled weights, zero bias / residual padding)
-              uint32_t xp = pack_bf16x2(__uint_as_float(v[g * 8 + 2 * j]) + bf16_lo(bw[j]),
-                                        __uint_as_float(v[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
-              if (p.R) xp = hadd2_bf16(xp, rw[g * 4 + j]);
-              ss = fmaf(bf16_lo(xp), bf16_lo(xp), ss);
-              ss = fmaf(bf16_hi(xp), bf16_hi(xp), ss);
-              xs[c * 16 + g * 4 + j] = xp;
-            }
-          }
-          if (p.Y) {
-            if (p.ncthw) {
-              if (ok_own) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int ch = col0 + 2 * j;
-                  if (ch < p.Cout)
-                    p.Y[(long long)ch * p.To * frame + pos_own] =
-                        __ushort_as_bfloat16((unsigned short)(xs[c * 16 + j] & 0xFFFFu));
-                  if (ch + 1 < p.Cout)
-                    p.Y[(long long)(ch + 1) * p.To * frame + pos_own] =
-                        __ushort_as_bfloat16((unsigned short)(xs[c * 16 + j] >> 16));
-                }
-              }
-            } else {
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                *reinterpret_cast<uint4*>(stg + lane * HALO_STG_PITCH + g * 16) =
-                    make_uint4(xs[c * 16 + g * 4], xs[c * 16 + g * 4 + 1], xs[c * 16 + g * 4 + 2],
-                               xs[c * 16 + g * 4 + 3]);
-              __syncwarp();
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (ok_co[i] && col0 + cv * 8 < p.cout_store)
-                  *reinterpret_cast<uint4*>(p.Y + pos_co[i] * p.ldy + col0 + cv * 8) =
-                      *reinterpret_cast<const uint4*>(stg + ((lane >> 2) + 8 * i) * HALO_STG_PITCH + cv * 16);
-              }
-              __syncwarp();
-            }
-          }
-        }
-      }
-      // accumulator fully read: hand it back before the second (register-only) pass
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      conv_epilogue_rows<NCH>(p, t_addr, 0, stg, lane, frame, pos_own, ok_own, pos_co, ok_co, tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      if (p.Y2) {
-        const float rinv = sqrtf((float)p.Cout) / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int col0 = c * 32;
-          if (col0 < p.cout_store) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int cg = col0 + g * 8;
-              uint4 gv = make_uint4(0, 0, 0, 0);
-              if (cg < p.cout_store) gv = __ldg(reinterpret_cast<const uint4*>(p.gamma + cg));
-              const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-              uint32_t o[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float y0 = bf16_lo(xs[c * 16 + g * 4 + j]) * rinv * bf16_lo(gw[j]);
-                float y1 = bf16_hi(xs[c * 16 + g * 4 + j]) * rinv * bf16_hi(gw[j]);
-                if (p.silu) {
-                  y0 = silu_fast(y0);
-                  y1 = silu_fast(y1);
-                }
-                o[j] = pack_bf16x2(y0, y1);
-              }
-              *reinterpret_cast<uint4*>(stg + lane * HALO_STG_PITCH + g * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (ok_co[i] && col0 + cv * 8 < p.cout_store)
-                *reinterpret_cast<uint4*>(p.Y2 + pos_co[i] * p.ldy2 + col0 + cv * 8) =
-                    *reinterpret_cast<const uint4*>(stg + ((lane >> 2) + 8 * i) * HALO_STG_PITCH + cv * 16);
-            }
-            __syncwarp();
-          }
-        }
-      }
     }
   }
 
@@ -582,6 +557,15 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
   }
+}
+
+template <int NCH>
+static int launch_taps(const ConvMaps& maps, const ConvParams& p, int smem, int grid, cudaStream_t s) {
+  auto kern = gf_conv3d_kernel<NCH>;
+  static bool configured[64] = {};
+  if (int e = gf_set_smem_once(configured, reinterpret_cast<const void*>(kern), 227 * 1024)) return e;
+  kern<<<grid, CONV_THREADS, smem, s>>>(maps, p);
+  return (int)cudaGetLastError();
 }
 
 template <int NCH>
@@ -614,7 +598,7 @@ extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int 
     return GF_ERR_BAD_ARG;
   const int cout_store = (Cout + 7) & ~7;
   if (!out_ncthw && Y && ((ldy % 8) || ldy < cout_store)) return GF_ERR_BAD_ARG;
-  if (out_ncthw && (R || Y2)) return GF_ERR_UNSUPPORTED;
+  if (out_ncthw && (R || Y2 || Cout > 32)) return GF_ERR_UNSUPPORTED;
   if (R && ((ldr % 8) || ldr < cout_store)) return GF_ERR_BAD_ARG;
   if (Y2 && (!gamma || (ldy2 % 8) || ldy2 < cout_store)) return GF_ERR_BAD_ARG;
 
@@ -670,8 +654,8 @@ extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int 
     p.bw_shift = 3;
     p.nWt = (Wo + HALO_W - 1) / HALO_W;
     p.nHt = (Ho + HALO_H - 1) / HALO_H;
-    const int fixed = HALO_A_STAGES * HALO_STAGE_BYTES + 8 * HALO_STG_BYTES + 1024 + 512;
-    p.stages = (224 * 1024 - fixed) / (p.BN * 128);
+    const int fixed = HALO_A_STAGES * HALO_STAGE_BYTES + 8 * CONV_STG_BYTES + 1024 + 512;
+    p.stages = (224 * 1024 - fixed) / (3 * p.BN * 128);       // B stages of one window row (3 taps) each
     if (p.stages > HALO_MAX_B_STAGES) p.stages = HALO_MAX_B_STAGES;
     ConvMaps hm;
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)T};
@@ -683,7 +667,7 @@ extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int 
     hrc = gf_make_tmap_2d_bf16(&hm.b, Wt, (uint64_t)p.ntaps * Cin, (uint64_t)Cout, (uint64_t)p.ntaps * Cin, CONV_BK,
                                (uint32_t)p.BN);
     if (hrc) return hrc;
-    const int hsmem = fixed + p.stages * p.BN * 128;
+    const int hsmem = fixed + p.stages * 3 * p.BN * 128;
     const long long htiles = (long long)To * p.nWt * p.nHt;
     int hgrid = gf_num_sms();
     if (hgrid <= 0) return GF_ERR_NO_DRIVER;
@@ -716,13 +700,11 @@ extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int 
                             (uint32_t)p.BN);
   if (rc) return rc;
 
-  const int smem = p.stages * stage_bytes + 1024 + 256;
-  static bool configured[64] = {};
-  if (int e = gf_set_smem_once(configured, reinterpret_cast<const void*>(gf_conv3d_kernel), 227 * 1024)) return e;
+  const int smem = p.stages * stage_bytes + 4 * CONV_STG_BYTES + 1024 + 256;
   const long long tiles = (long long)To * p.nWt * p.nHt * p.num_n_tiles;
   int grid = gf_num_sms();
   if (grid <= 0) return GF_ERR_NO_DRIVER;
   if (grid > tiles) grid = (int)tiles;
-  gf_conv3d_kernel<<<grid, CONV_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, p);
-  return (int)cudaGetLastError();
+  cudaStream_t cs = reinterpret_cast<cudaStream_t>(stream);
+  return p.BN <= 128 ? launch_taps<4>(maps, p, smem, grid, cs) : launch_taps<8>(maps, p, smem, grid, cs);
 }

@@ -107,7 +107,12 @@ class WanVideoVAEB200:
         """next_norm: (gamma, silu) of the consumer's RMS_norm.  Returns (raw or None, normed or None)."""
         cv = self.conv[name]
         cout = cv.cout if cout is None else cout
-        fuse = next_norm is not None and cout <= FUSE_MAX_CHANNELS and not ncthw
+        # Fusing the consumer's RMS_norm pays under a full 27-tap window, where the longer epilogue hides behind the
+        # MMAs of the next tile.  The 9-tap resample convolutions have a third of the MMA time per tile: there the
+        # fused epilogue becomes the critical path and costs more than the separate norm kernel (measured with
+        # tools/conv_bench.py --fused: 192->96 at 81x480x832 8.6 ms + 2.3 ms unfused vs 12.3 ms fused).
+        kt, kh, kw = cv.kernel
+        fuse = next_norm is not None and cout <= FUSE_MAX_CHANNELS and not ncthw and kt * kh * kw >= 27
         w = cv.w if cout == cv.cout else cv.w[:cout]
         y, yn = capi.conv3d_cl(x, w, cv.bias, kernel=cv.kernel, stride=stride, pad=pad, out_dims=out_dims, out=out,
                                residual=residual, gamma=next_norm[0] if fuse else None,
