@@ -56,7 +56,7 @@ SIGNATURES = {
     "gf_vae_rmsnorm_bf16": [_p, _ll, _p, _ll, _ll, _i, _p, _i, _p],
     "gf_vae_upsample2x_bf16": [_p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p],
     "gf_softmax_f32_bf16": [_p, _ll, _p, _ll, _i, _i, _i, _f, _p],
-    "gf_vae_planes_to_cl_bf16": [_p, _ll, _i, _p, _ll, _i, _p, _p, _i, _p],
+    "gf_vae_planes_to_cl_bf16": [_p, _ll, _i, _p, _ll, _i, _p, _p, _i, _i, _i, _p],
     "gf_vae_cl_to_planes_bf16": [_p, _ll, _ll, _i, _p, _p, _p, _i, _p],
     "gf_vae_blend_bf16": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p],
     "gf_vae_blend_finish_bf16": [_p, _ll, _i, _i, _p, _i, _p],
@@ -593,19 +593,22 @@ def softmax_f32(S: torch.Tensor, P: torch.Tensor, L: int, Lp: int, scale: float)
 
 
 def vae_planes_to_cl(src: torch.Tensor, Cp: int, *, mean: torch.Tensor | None = None,
-                     inv_std: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
-    """src: (C, T, H, W) contiguous bf16 -> [T, H, W, Cp] channels-last (zero-padded channels)."""
+                     inv_std: torch.Tensor | None = None, out: torch.Tensor | None = None, wpad: int = 0) -> torch.Tensor:
+    """src: (C, T, H, W) contiguous bf16 -> [T, H, W, Cp] channels-last (zero-padded channels).  wpad > 0: `out` is a
+    zero-filled [T, H, W + 2*wpad, Cp] buffer and the clip lands in its columns [wpad, wpad + W)."""
     _req(src, "src")
     if not src.is_contiguous():
         raise ValueError("vae_planes_to_cl: src must be contiguous")
     C, T, H, W = src.shape
+    if wpad and (out is None or out.shape != (T, H, W + 2 * wpad, Cp) or not out.is_contiguous()):
+        raise ValueError("vae_planes_to_cl: wpad needs a contiguous [T, H, W + 2*wpad, Cp] destination")
     if out is None:
         out = torch.empty((T, H, W, Cp), dtype=torch.bfloat16, device=src.device)
     mode = 0 if mean is None else 1
     if mode:
         _req(mean, "mean", torch.float32); _req(inv_std, "inv_std", torch.float32)
     _call("vae_rowwise", 2.0 * T * H * W * (C + Cp), load().gf_vae_planes_to_cl_bf16, src.data_ptr(), T * H * W, C,
-          out.data_ptr(), out.stride(2), Cp, _ptr(mean), _ptr(inv_std), mode, _stream())
+          out.data_ptr(), out.stride(2), Cp, _ptr(mean), _ptr(inv_std), mode, W if wpad else 0, wpad, _stream())
     return out
 
 

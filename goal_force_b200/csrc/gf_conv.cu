@@ -588,7 +588,7 @@ extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int 
                                  void* stream) {
   using namespace gf;
   if (!X || !Wt || (!Y && !Y2) || T <= 0 || H <= 0 || W <= 0 || To <= 0 || Ho <= 0 || Wo <= 0) return GF_ERR_BAD_ARG;
-  if (Cin <= 0 || (Cin % 8) || (ldx % 8) || ldx < Cin || Cout <= 0) return GF_ERR_BAD_ARG;
+  if (Cin <= 0 || (Cin % 8) || (ldx % 8) || ldx <= 0 || Cout <= 0) return GF_ERR_BAD_ARG;   // ldx < Cin: overlapping windows
   if (kt < 1 || kh < 1 || kw < 1 || kt * kh * kw > CONV_MAX_TAPS) return GF_ERR_UNSUPPORTED;
   if (st < 1 || sh < 1 || sh > 2 || sw != sh) return GF_ERR_UNSUPPORTED;
   if (pt < 0 || ph < 0 || pw < 0 || pt > 8 || ph > 8 || pw > 8) return GF_ERR_BAD_ARG;

@@ -148,13 +148,20 @@ __global__ void vae_softmax_kernel(const float* __restrict__ S, long long lds, _
 // un-normalisation z / inv_std + mean (VideoVAE_.decode :1014-1018: z / scale[1] + scale[0], bf16 after each op).
 __global__ void vae_planes_to_cl_kernel(const __nv_bfloat16* __restrict__ src, long long N, int C,
                                         __nv_bfloat16* __restrict__ dst, long long ldo, int Cp,
-                                        const float* __restrict__ mean, const float* __restrict__ inv_std, int mode) {
+                                        const float* __restrict__ mean, const float* __restrict__ inv_std, int mode,
+                                        int row_w, int wpad) {
   const int nvec = Cp >> 3;
   const long long total = N * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / nvec;                  // consecutive threads: consecutive positions of one channel group
     const int vi = (int)(i % nvec);
+    // destination position: dense, or rows of row_w positions with wpad untouched positions on either side
+    long long nd = n;
+    if (row_w > 0) {                               // 32-bit division (N < 2^31 is checked on the host)
+      const unsigned row = (unsigned)n / (unsigned)row_w;
+      nd = (long long)row * (row_w + 2 * wpad) + ((unsigned)n - row * (unsigned)row_w) + wpad;
+    }
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -166,7 +173,7 @@ __global__ void vae_planes_to_cl_kernel(const __nv_bfloat16* __restrict__ src, l
       }
       x[j] = v;
     }
-    *reinterpret_cast<uint4*>(dst + n * ldo + vi * 8) =
+    *reinterpret_cast<uint4*>(dst + nd * ldo + vi * 8) =
         make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
   }
 }
@@ -268,14 +275,17 @@ extern "C" int gf_softmax_f32_bf16(const float* S, long long lds, void* P, long 
 }
 
 extern "C" int gf_vae_planes_to_cl_bf16(const void* src, long long N, int C, void* dst, long long ldo, int Cp,
-                                        const float* mean, const float* inv_std, int mode, void* stream) {
+                                        const float* mean, const float* inv_std, int mode, int row_w, int wpad,
+                                        void* stream) {
   if (!src || !dst || N <= 0 || C <= 0 || Cp < C || (Cp % 8) || (ldo % 8) || ldo < Cp) return GF_ERR_BAD_ARG;
+  if (row_w < 0 || wpad < 0 || (row_w == 0 && wpad != 0) || (row_w > 0 && (N % row_w || N >= (1ll << 31))))
+    return GF_ERR_BAD_ARG;
   if (mode != 0 && mode != 1) return GF_ERR_BAD_ARG;
   if (mode == 1 && (!mean || !inv_std)) return GF_ERR_BAD_ARG;
   const long long total = N * (Cp / 8);
   vae_planes_to_cl_kernel<<<stream_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(src), N, C, reinterpret_cast<__nv_bfloat16*>(dst), ldo, Cp, mean, inv_std,
-      mode);
+      mode, row_w, wpad);
   return (int)cudaGetLastError();
 }
 

@@ -93,6 +93,16 @@ class WanVideoVAEB200:
                     "bo": state_dict[pre + ".proj.bias"].detach().to(device=self.device, dtype=torch.bfloat16).contiguous(),
                 }
         self._masks: dict = {}
+        # encoder.conv1 reads 3 (padded to 8) channels: as a 27-tap convolution every k-block would carry 8 useful
+        # channels of 64.  Folded form: the clip is stored with one zero position left and right of every row, and a
+        # position's operand row is the 64-element window [w, w + 8) x 8 channels of that padded row (position pitch 8
+        # < Cin 64: overlapping windows).  The three dw taps become columns 0..23 of a (dt, dh)-tap weight, the rest
+        # of the window meets zero weights: 9 k-blocks of 64 instead of 27.
+        w = state_dict["encoder.conv1.weight"].detach().to(device=self.device, dtype=torch.float32)   # [C, 3, 3, 3, 3]
+        cout, cin = w.shape[0], w.shape[1]
+        wf = torch.zeros((cout, 3, 3, 8, 8), dtype=torch.float32, device=self.device)                 # [co, dt, dh, dw, c]
+        wf[:, :, :, :3, :cin] = w.permute(0, 2, 3, 4, 1)
+        self.conv1_folded = wf.reshape(cout, 9 * 64).to(torch.bfloat16).contiguous()
 
     @classmethod
     def from_reference(cls, vae, device="cuda"):
@@ -242,8 +252,14 @@ class WanVideoVAEB200:
                 seq.append(("down", f"{p}downsamples.{idx}", self.temporal_down[i]))
                 idx += 1
         seq.append(("res", p + "middle.0", False))
-        x = capi.vae_planes_to_cl(video, _round8(video.shape[0]))
-        x, xn = self._conv3d(p + "conv1", x, pad=(2, 1, 1), next_norm=(self.gamma[seq[0][1] + ".residual.0"], True))
+        C, T, H, W = video.shape
+        padded = torch.zeros((T * H * (W + 2) + 8) * 8, dtype=torch.bfloat16, device=video.device)    # + window slack
+        capi.vae_planes_to_cl(video, 8, out=padded[: T * H * (W + 2) * 8].view(T, H, W + 2, 8), wpad=1)
+        windows = torch.as_strided(padded, (T, H, W + 2, 64), (H * (W + 2) * 8, (W + 2) * 8, 8, 1))
+        cv = self.conv[p + "conv1"]
+        x, _ = capi.conv3d_cl(windows, self.conv1_folded, cv.bias, kernel=(3, 3, 1), pad=(2, 1, 0), out_dims=(T, H, W))
+        xn = capi.vae_rmsnorm(x, self.gamma[seq[0][1] + ".residual.0"], silu=True)
+        del padded, windows
         for j, (kind, name, temporal) in enumerate(seq):
             if j + 1 < len(seq):
                 nk, nn_, _ = seq[j + 1]

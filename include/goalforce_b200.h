@@ -157,6 +157,8 @@ int gf_t5_attention_bf16(const void* Q, long long ldq, const void* K, long long 
  *   Y[to,ho,wo,co] = sum Wt[co][(dt,dh,dw)][ci] * X[to*st + dt - pt, ho*sh + dh - ph, wo*sw + dw - pw, ci]  (+ bias)
  * Input positions outside the clip read as zero, so pt/ph/pw are the leading paddings (pt = kt-1 is the causal form)
  * and the trailing padding follows from To/Ho/Wo.  Wt: [Cout][kt*kh*kw][Cin] bf16, Cin % 8 == 0; sh == sw in {1, 2}.
+ * ldx < Cin is allowed: every position then sees a window of Cin elements that overlaps its right-hand neighbours
+ * (the 3-channel input convolution folds its three dw taps into one 64-element window this way).
  * R (optional): residual [To*Ho*Wo][ldr] added after the bias (ResidualBlock :296-301).
  * Y2/gamma (optional, Cout <= 256): Y2 = act(RMS_norm(Y) * gamma) of the NEXT layer (:55-70), act = SiLU when silu != 0;
  * Y may be NULL when only Y2 is wanted.  out_ncthw != 0: Y is (Cout, To, Ho, Wo) planes (the 3-channel decoder head).
@@ -184,9 +186,11 @@ int gf_softmax_f32_bf16(const float* S, long long lds, void* P, long long ldp, i
 
 /* (C, N) planes <-> channels-last rows.  planes_to_cl pads channels [C, Cp) with zeros; mode 1 applies the latent
  * un-normalisation z / inv_std + mean of VideoVAE_.decode (:1014-1018).  cl_to_planes mode 1 applies
- * (mu - mean) * inv_std of VideoVAE_.encode (:1003-1007).  mean / inv_std: fp32 [C] on the device. */
+ * (mu - mean) * inv_std of VideoVAE_.encode (:1003-1007).  mean / inv_std: fp32 [C] on the device.
+ * row_w > 0: the destination has rows of row_w + 2*wpad positions and source position n lands at column n % row_w + wpad
+ * of row n / row_w (the border positions are left untouched: the caller zero-fills them once). */
 int gf_vae_planes_to_cl_bf16(const void* src, long long N, int C, void* dst, long long ldo, int Cp, const float* mean,
-                             const float* inv_std, int mode, void* stream);
+                             const float* inv_std, int mode, int row_w, int wpad, void* stream);
 int gf_vae_cl_to_planes_bf16(const void* src, long long ld, long long N, int C, void* dst, const float* mean,
                              const float* inv_std, int mode, void* stream);
 

@@ -139,6 +139,10 @@ def test_rowwise_kernels_against_torch(capi):
     v3 = _bf(torch.randn(3, 2, 4, 6, generator=g)).cuda()
     cl3 = capi.vae_planes_to_cl(v3, 8)
     assert torch.equal(cl3[..., :3].permute(3, 0, 1, 2), v3) and float(cl3[..., 3:].abs().max()) == 0.0
+    padded = torch.zeros(2, 4, 6 + 2, 8, dtype=torch.bfloat16, device="cuda")
+    capi.vae_planes_to_cl(v3, 8, out=padded, wpad=1)
+    assert torch.equal(padded[:, :, 1:-1, :3].permute(3, 0, 1, 2), v3)
+    assert float(padded[:, :, 0].abs().max()) == 0.0 and float(padded[:, :, -1].abs().max()) == 0.0
     back = capi.vae_cl_to_planes(cl, 16, mean=mean, inv_std=inv_std)
     wantb = _bf(_bf(cl.permute(3, 0, 1, 2) - _bf(mean).view(-1, 1, 1, 1)) * _bf(inv_std).view(-1, 1, 1, 1))
     assert torch.equal(back, wantb)
