@@ -148,6 +148,31 @@ class BatchDriver:
         return jobs
 
 
+def vae_control_encoder(vae, tiled: bool = True, tile_size=(30, 52), tile_stride=(15, 26)):
+    """`encode_control` on the B200 VAE (goal_force_b200.wan_vae.WanVideoVAEB200): what
+    WanVideoUnit_ControlVideoEmbedder.process does (src/goal_force/wan_video_new.py:798-805) -- the (F, H, W, 3) control
+    video goes in as it is, rearranged to (1, 3, F, H, W), and comes back as (1, 16, T, H/8, W/8) bf16 latents; the
+    tiling defaults are the pipeline's (:648-650)."""
+
+    def encode(video: torch.Tensor) -> torch.Tensor:
+        v = video.to(device=vae.device, dtype=torch.bfloat16).permute(3, 0, 1, 2).unsqueeze(0)
+        return vae.encode(v, vae.device, tiled=tiled, tile_size=tile_size, tile_stride=tile_stride)
+
+    return encode
+
+
+def vae_image_condition(vae, image: torch.Tensor, num_frames: int, tiled: bool = True, tile_size=(30, 52),
+                        tile_stride=(15, 26)) -> torch.Tensor:
+    """`y` of WanVideoUnit_ImageEmbedderVAE.process (src/goal_force/wan_video_new.py:894-916) on the B200 VAE:
+    image (3, H, W) in [-1, 1] -> first frame of an otherwise zero clip -> VAE encode -> cat(mask, latents)[None]."""
+    from .pipeline import image_condition
+    c, h, w = image.shape
+    clip = torch.zeros((c, num_frames, h, w), dtype=torch.bfloat16, device=vae.device)
+    clip[:, 0] = image.to(device=vae.device, dtype=torch.bfloat16)
+    lat = vae.encode([clip], vae.device, tiled=tiled, tile_size=tile_size, tile_stride=tile_stride)[0]
+    return image_condition(lat, num_frames)
+
+
 def synthetic_control_encoder(device="cuda"):
     """Stand-in for `VAE.encode(control video)` where no VAE weights exist (benchmarks, tests): a fixed linear map
     with the VAE's shape contract, (F, H, W, 3) in [0, 1] -> (1, 16, (F-1)/4+1, H/8, W/8) bf16: 8x8 spatial / 4-frame

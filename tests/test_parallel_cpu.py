@@ -49,7 +49,9 @@ def _install_kernel_doubles():
         out.copy_(res)
         return out
 
-    def attention(q, k, v, heads, out=None, scale=None):
+    def attention(q, k, v, heads, out=None, scale=None, kv_len=None):
+        if kv_len is not None:                       # zero-padded token tail: attend to the real keys only
+            k, v = k[:kv_len], v[:kv_len]
         res = _attn_ref(q, k, v, heads)
         if out is None:
             return res
@@ -93,8 +95,17 @@ def _worker_ulysses(rank, world, port, L, heads):
         # second call reuses the cached exchange buffers
         sp.self_attention(qkv[sl].contiguous(), heads, out)
         assert torch.equal(out, full[sl])
-        with pytest.raises(ValueError):
-            sp.token_slice(L + 1)
+        # a token count that does not divide: ceil(L/P) rows per rank, zero-padded tail, padded keys masked (kv_len)
+        Lo = L + 1
+        n = sp.rows_per_rank(Lo)
+        assert n == -(-Lo // world)
+        qkv_o = torch.randn(Lo, 3 * d, generator=g).bfloat16()
+        full_o = _attn_ref(qkv_o[:, :d], qkv_o[:, d:2 * d], qkv_o[:, 2 * d:], heads)
+        slo = sp.token_slice(Lo)
+        assert slo.start == min(rank * n, Lo) and slo.stop == min((rank + 1) * n, Lo)
+        out_o = torch.empty(n, d, dtype=torch.bfloat16)
+        sp.self_attention(sp.shard_rows(qkv_o, Lo), heads, out_o, 0, Lo)
+        assert torch.equal(out_o[: slo.stop - slo.start], full_o[slo])
         with pytest.raises(ValueError):
             sp.self_attention(torch.randn(4, 3 * 3 * 128).bfloat16(), 3, torch.empty(4, 3 * 128).bfloat16())   # 3 heads over 2 ranks
     finally:

@@ -93,6 +93,47 @@ def main():
     xq = torch.randn(33, 8 * 128, device=dev).bfloat16()
     pk = capi.ulysses_pack(xq, 8, 128, 4)
     check("ulysses pack/unpack", 0.0 if torch.equal(capi.ulysses_unpack(pk, 33, 8, 128, 4), xq) else 1.0, 0.0)
+    # ---- Wan VAE pieces: both convolution kernels (ragged frames), strided maps, streaming kernels, a tiny clip
+    torch.backends.cudnn.allow_tf32 = False
+
+    def conv_case(name, cin, cout, dims, kernel, stride, pad, fused):
+        T, H, W = dims
+        taps = kernel[0] * kernel[1] * kernel[2]
+        xc = torch.randn(cin, T, H, W, device=dev).bfloat16()
+        wc = (torch.randn(cout, cin, *kernel, device=dev) / math.sqrt(cin * taps)).bfloat16()
+        bc = torch.zeros((cout + 7) // 8 * 8, device=dev).bfloat16()
+        if stride[1] == 2:
+            xp, Ho, Wo = F.pad(xc.float(), (0, 1, 0, 1, pad[0], 0)), H // 2, W // 2
+        else:
+            xp = F.pad(xc.float(), (pad[2], kernel[2] - 1 - pad[2], pad[1], kernel[1] - 1 - pad[1], pad[0], 0))
+            Ho, Wo = H, W
+        want = F.conv3d(xp[None], wc.float(), None, stride=stride)[0]
+        gam = torch.ones((cout + 7) // 8 * 8, device=dev).bfloat16() if fused else None
+        res = torch.randn(want.shape[1], Ho, Wo, cout, device=dev).bfloat16() if fused else None
+        yv, _ = capi.conv3d_cl(xc.permute(1, 2, 3, 0).contiguous(), wc.permute(0, 2, 3, 4, 1).reshape(cout, -1).contiguous(),
+                               bc, kernel=kernel, stride=stride, pad=pad, out_dims=(want.shape[1], Ho, Wo), residual=res,
+                               gamma=gam, cout=cout)
+        if fused:
+            want = want.bfloat16().float() + res.permute(3, 0, 1, 2).float()
+        check(name, rel(yv.permute(3, 0, 1, 2)[:cout], want), 6e-3)
+
+    conv_case("conv halo 96>96 fused", 96, 96, (3, 19, 13), (3, 3, 3), (1, 1, 1), (2, 1, 1), True)
+    conv_case("conv halo 16>32", 16, 32, (2, 9, 11), (3, 3, 3), (1, 1, 1), (2, 1, 1), False)
+    conv_case("conv taps 192>192 fused", 192, 192, (3, 9, 13), (3, 3, 3), (1, 1, 1), (2, 1, 1), True)
+    conv_case("conv taps 192>384", 192, 384, (2, 7, 9), (3, 3, 3), (1, 1, 1), (2, 1, 1), False)
+    conv_case("conv stride2 96>96", 96, 96, (2, 10, 14), (1, 3, 3), (1, 2, 2), (0, 0, 0), False)
+    conv_case("conv time stride2", 64, 64, (7, 5, 6), (3, 1, 1), (2, 1, 1), (0, 0, 0), False)
+    from goal_force_b200.wan_vae import WanVideoVAEB200
+    from oracle import wan_vae_oracle as V
+    sd = V.random_state_dict(dim=32, seed=0)
+    vae = WanVideoVAEB200(sd, dim=32)
+    zz = torch.randn(1, 16, 2, 5, 6)
+    with torch.no_grad():
+        check("vae decode (dim 32)", rel(vae._decode_clip(zz[0].to(dev).bfloat16()).cpu(), V.decode(sd, zz, dim=32)[0]), 3e-2)
+        vid = torch.randn(1, 3, 5, 24, 40).clamp(-1, 1)
+        check("vae encode (dim 32)", rel(vae._encode_clip(vid[0].to(dev).bfloat16()).cpu(), V.encode(sd, vid, dim=32)[0]), 3e-2)
+        check("vae tiled decode", rel(vae.decode(zz.bfloat16(), dev, tiled=True, tile_size=(4, 4), tile_stride=(2, 3)).cpu(),
+                                      V.tiled_decode(sd, zz, (4, 4), (2, 3), dim=32)), 3e-2)
     torch.cuda.synchronize()
     print("ALL OK" if ok else "FAILURES", flush=True)
     return 0 if ok else 1
