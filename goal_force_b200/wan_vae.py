@@ -311,7 +311,27 @@ class WanVideoVAEB200:
     def _prep(self, t: torch.Tensor) -> torch.Tensor:
         return t.to(device=self.device, dtype=torch.bfloat16).contiguous()
 
-    def tiled_decode(self, hidden_states, device=None, tile_size=(34, 34), tile_stride=(18, 16)):
+    def _tiles(self, tasks, fn, shape_of, group):
+        """Yield (task, tile) in the reference's task order.  With a process group the tiles are computed round-robin
+        by its ranks and broadcast from their owners (NCCL over NVLink), so every rank blends the same tiles in the
+        same order and ends up with the bit-identical result of the single-GPU loop."""
+        if group is None:
+            for task in tasks:
+                yield task, fn(task)
+            return
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        mine = {i: fn(task) for i, task in enumerate(tasks) if i % world == rank}
+        for i, task in enumerate(tasks):
+            tile = mine.pop(i, None)
+            if tile is None:
+                tile = torch.empty(shape_of(task), dtype=torch.bfloat16, device=self.device)
+            dist.broadcast(tile, src=dist.get_global_rank(group, i % world), group=group)
+            yield task, tile
+
+    def tiled_decode(self, hidden_states, device=None, tile_size=(34, 34), tile_stride=(18, 16), group=None):
+        """`group`: optional torch.distributed process group whose ranks all hold `hidden_states` (the replica group
+        after denoising); the tiles are then decoded round-robin across its GPUs."""
         _, _, T, H, W = hidden_states.shape
         up = self.upsampling_factor
         z = self._prep(hidden_states[0])
@@ -320,18 +340,26 @@ class WanVideoVAEB200:
         weight = torch.zeros((1, 1, H * up, W * up), dtype=torch.bfloat16, device=self.device)
         border = ((tile_size[0] - tile_stride[0]) * up, (tile_size[1] - tile_stride[1]) * up)
         ones = {}
-        for h, h_, w, w_ in self._tasks(H, W, tile_size, tile_stride):
-            tile = self._decode_clip(z[:, :, h:h_, w:w_].contiguous())
+        tasks = self._tasks(H, W, tile_size, tile_stride)
+
+        def shape_of(task):
+            h, h_, w, w_ = task
+            return (3, out_T, (min(h_, H) - h) * up, (min(w_, W) - w) * up)
+
+        def decode_tile(task):
+            h, h_, w, w_ = task
+            return self._decode_clip(z[:, :, h:h_, w:w_].contiguous())
+
+        for (h, h_, w, w_), tile in self._tiles(tasks, decode_tile, shape_of, group):
             mask = self.build_mask(tile, (h == 0, h_ >= H, w == 0, w_ >= W), border)
             capi.vae_blend_(values, tile, mask, h * up, w * up)
             one = ones.setdefault(tuple(mask.shape), torch.ones((1, 1) + tuple(mask.shape), dtype=torch.bfloat16,
                                                                 device=self.device))
             capi.vae_blend_(weight, one, mask, h * up, w * up)
-            del tile
         capi.vae_blend_finish_(values, weight.view(H * up, W * up), clamp=True)
         return values.unsqueeze(0)
 
-    def tiled_encode(self, video, device=None, tile_size=(272, 272), tile_stride=(144, 128)):
+    def tiled_encode(self, video, device=None, tile_size=(272, 272), tile_stride=(144, 128), group=None):
         """tile sizes in pixels (the public `encode` multiplies the latent-unit arguments by 8, as the reference)."""
         _, _, T, H, W = video.shape
         up = self.upsampling_factor
@@ -341,8 +369,17 @@ class WanVideoVAEB200:
         weight = torch.zeros((1, 1, H // up, W // up), dtype=torch.bfloat16, device=self.device)
         border = ((tile_size[0] - tile_stride[0]) // up, (tile_size[1] - tile_stride[1]) // up)
         ones = {}
-        for h, h_, w, w_ in self._tasks(H, W, tile_size, tile_stride):
-            tile = self._encode_clip(v[:, :, h:h_, w:w_].contiguous())
+        tasks = self._tasks(H, W, tile_size, tile_stride)
+
+        def shape_of(task):
+            h, h_, w, w_ = task
+            return (self.z_dim, out_T, (min(h_, H) - h) // up, (min(w_, W) - w) // up)
+
+        def encode_tile(task):
+            h, h_, w, w_ = task
+            return self._encode_clip(v[:, :, h:h_, w:w_].contiguous())
+
+        for (h, h_, w, w_), tile in self._tiles(tasks, encode_tile, shape_of, group):
             mask = self.build_mask(tile, (h == 0, h_ >= H, w == 0, w_ >= W), border)
             capi.vae_blend_(values, tile, mask, h // up, w // up)
             one = ones.setdefault(tuple(mask.shape), torch.ones((1, 1) + tuple(mask.shape), dtype=torch.bfloat16,
@@ -359,25 +396,25 @@ class WanVideoVAEB200:
         capi.vae_blend_finish_(video, None, clamp=True)
         return video.unsqueeze(0)
 
-    def encode(self, videos, device=None, tiled=False, tile_size=(34, 34), tile_stride=(18, 16)):
+    def encode(self, videos, device=None, tiled=False, tile_size=(34, 34), tile_stride=(18, 16), group=None):
         hidden_states = []
         for video in videos:
             video = video.unsqueeze(0)
             if tiled:
                 ts = (tile_size[0] * self.upsampling_factor, tile_size[1] * self.upsampling_factor)
                 st = (tile_stride[0] * self.upsampling_factor, tile_stride[1] * self.upsampling_factor)
-                hidden_state = self.tiled_encode(video, device, ts, st)
+                hidden_state = self.tiled_encode(video, device, ts, st, group=group)
             else:
                 hidden_state = self.single_encode(video, device)
             hidden_states.append(hidden_state.squeeze(0))
         return torch.stack(hidden_states)
 
-    def decode(self, hidden_states, device=None, tiled=False, tile_size=(34, 34), tile_stride=(18, 16)):
+    def decode(self, hidden_states, device=None, tiled=False, tile_size=(34, 34), tile_stride=(18, 16), group=None):
         videos = []
         for hidden_state in hidden_states:
             hidden_state = hidden_state.unsqueeze(0)
             if tiled:
-                video = self.tiled_decode(hidden_state, device, tile_size, tile_stride)
+                video = self.tiled_decode(hidden_state, device, tile_size, tile_stride, group=group)
             else:
                 video = self.single_decode(hidden_state, device)
             videos.append(video.squeeze(0))

@@ -38,7 +38,22 @@ def _worker(rank, world, port, mode, transport, ret, shape=(4, 40, 52)):
         cn = ControlNetB200(cfg, csd, 1, device=dev)
         kw = dict(dit=dit, controlnet=cn, latents=inp["latents"], timestep=inp["timestep"], context=inp["context"],
                   y=inp["y"], control_signal_video_latents=inp["control_signal_video_latents"])
-        if mode == "sp":
+        if mode == "vae":
+            # tiles of WanVideoVAE.tiled_decode / tiled_encode computed round-robin by the ranks and broadcast from
+            # their owners: every rank must end with the single-GPU result, bit for bit
+            from goal_force_b200.wan_vae import WanVideoVAEB200
+            from oracle import wan_vae_oracle as V
+            vae = WanVideoVAEB200(V.random_state_dict(dim=32, seed=0), dim=32, device=dev)
+            g = torch.Generator("cpu").manual_seed(5)
+            z = torch.randn(1, 16, 2, 9, 11, generator=g).to(dev, torch.bfloat16)
+            kw_t = dict(tiled=True, tile_size=(4, 5), tile_stride=(3, 3))
+            a = vae.decode(z, dev, **kw_t)
+            b = vae.decode(z, dev, group=dist.group.WORLD, **kw_t)
+            ea = vae.encode(a, dev, **kw_t)
+            eb = vae.encode(a, dev, group=dist.group.WORLD, **kw_t)
+            ok = bool(torch.equal(a, b) and torch.equal(ea, eb))
+            err = float((a.float() - b.float()).abs().max())
+        elif mode == "sp":
             par = ParallelContext(ParallelLayout(world_size=world, rank=rank, cfg_size=1), transport=transport)
             single = model_fn_wan_video(**kw)
             multi = model_fn_wan_video(sequence_parallel=par.sp, **kw)
@@ -112,3 +127,10 @@ def test_ulysses_token_count_not_divisible(lib, transport):
     over 2 ranks = 68 + 67 (+1 zero row).  The padding row is masked out of the keys, so the result still equals the
     unsharded forward bit for bit."""
     _run("sp", transport, 2, shape=(3, 10, 18))
+
+
+@pytest.mark.timeout(900)
+def test_vae_tiles_sharded_over_ranks_bit_identical(lib):
+    """Wan VAE tiled decode / encode with the tiles spread over 2 GPUs (12 tiles of a 9 x 11 latent) against the
+    single-GPU loop."""
+    _run("vae", "nccl", 2)
