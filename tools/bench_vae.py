@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--frames", type=int, default=81)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=832)
+    ap.add_argument("--launch-list", action="store_true", help="one untimed single decode + encode (ncu launch-list pass)")
     a = ap.parse_args()
     from goal_force_b200.wan_vae import WanVideoVAEB200
     from oracle import wan_vae_oracle as V
@@ -78,6 +79,11 @@ def main():
         finally:
             dump()
 
+    if a.launch_list:
+        vae.decode(z, "cuda", tiled=False)
+        vae.encode(video, "cuda", tiled=False)
+        torch.cuda.synchronize()
+        return
     tiled_dec = section("ours_tiled_decode", lambda: vae.decode(z, "cuda", tiled=True, tile_size=(30, 52), tile_stride=(15, 26)))
     single_dec = section("ours_single_decode", lambda: vae.decode(z, "cuda", tiled=False))
     section("ours_tiled_encode", lambda: vae.encode(video, "cuda", tiled=True, tile_size=(30, 52), tile_stride=(15, 26)))

@@ -58,7 +58,7 @@ def main():
             run()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / a.iters
+        ms = e0.elapsed_time(e1) / max(a.iters, 1)
         flops = 2.0 * T * H * W * cout * taps * cin
         res[name] = {"ms": round(ms, 3), "tflops": round(flops / ms / 1e9, 1), "gflop": round(flops / 1e9, 1),
                      "fused": fused}
