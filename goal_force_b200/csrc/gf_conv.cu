@@ -68,7 +68,7 @@ struct ConvParams {
 // registers, stores Y and hands the accumulator back; pass 1 (fused RMS_norm + SiLU of the next layer) works from the
 // registers.  R / Y / Y2 move through the warp's staging tile `stg` (32 rows x 80 B) so that every global access is a
 // 64-byte row segment: lane l owns row l in the math, and serves rows (l >> 2) + 8 i, 16-byte column (l & 3) in the I/O.
-template <int NCH>
+template <int NCH, bool kRemoteArrive = false>
 __device__ __forceinline__ void conv_epilogue_rows(const ConvParams& p, uint32_t t_addr, int n0, uint8_t* stg, int lane,
                                                    long long frame, long long pos_own, bool ok_own,
                                                    const long long (&pos_co)[4], const bool (&ok_co)[4],
@@ -155,7 +155,9 @@ __device__ __forceinline__ void conv_epilogue_rows(const ConvParams& p, uint32_t
   // accumulator fully read: hand it back before the second (register-only) pass
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(tempty_addr);
+  if (lane == 0) {
+    if constexpr (kRemoteArrive) mbar_arrive_cluster(tempty_addr); else mbar_arrive(tempty_addr);
+  }
   if (p.Y2) {
     const float rinv = sqrtf((float)p.Cout) / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
@@ -364,14 +366,15 @@ constexpr int HALO_ROWS = (HALO_W + 2) * (HALO_H + 2);   // 340
 constexpr int HALO_TX_BYTES = HALO_ROWS * 128;           // 43,520
 constexpr int HALO_STAGE_BYTES = 44 * 1024;
 constexpr int HALO_A_STAGES = 2;
-constexpr int HALO_MAX_B_STAGES = 4;
+constexpr int HALO_MAX_B_STAGES = 6;
 
-template <int NCH>
+template <int NCH, int kCG>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_tap_bytes = (uint32_t)p.BN * 128u;      // weights of one tap: BN rows x 64 channels
+  const uint32_t b_rows = (uint32_t)p.BN / kCG;            // weight rows staged by this CTA (pair: half of them each)
+  const uint32_t b_tap_bytes = b_rows * 128u;              // weights of one tap: b_rows x 64 channels
   const uint32_t b_bytes = 3u * b_tap_bytes;               // a B stage holds one window row (dw = 0, 1, 2)
   const uint32_t b_base = smem_base + HALO_A_STAGES * HALO_STAGE_BYTES;
   const uint32_t stg_base = b_base + p.stages * b_bytes;
@@ -387,7 +390,13 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
   auto smem_b = [&](int s) { return b_base + s * b_bytes; };
 
   const int warp = threadIdx.x >> 5;
-  const int tiles_per_frame = p.nWt * p.nHt;
+  const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x / kCG, num_clusters = gridDim.x / kCG;
+  // work unit of a CTA (pair): kCG horizontally adjacent 32 x 8 tiles; a pair's odd tile past the frame edge is all
+  // out-of-range positions (zero-filled loads, masked stores)
+  const int units_per_row = (p.nWt + kCG - 1) / kCG;
+  const int tiles_per_frame = units_per_row * p.nHt;
   const int num_tiles = p.To * tiles_per_frame;
   const int num_cb = (p.Cin + CONV_BK - 1) / CONV_BK;
   const int kt = p.ntaps / 9;
@@ -400,15 +409,15 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     if (elect_one()) {
       for (int s = 0; s < HALO_A_STAGES; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
       for (int s = 0; s < p.stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8 * kCG); }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc<1>(tmem_ptr_smem, 512);
-    tmem_relinquish<1>();
+    tmem_alloc<kCG>(tmem_ptr_smem, 512);
+    tmem_relinquish<kCG>();
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
@@ -418,25 +427,40 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     if (elect_one()) {
       int as = 0; uint32_t aphase = 0;
       int bs = 0; uint32_t bphase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const int tt = t / tiles_per_frame;
         const int rem = t - tt * tiles_per_frame;
-        const int ht = rem / p.nWt, wt = rem - ht * p.nWt;
+        const int ht = rem / units_per_row, wt = (rem - ht * units_per_row) * kCG + (int)cta_rank;
         const int h0 = ht * HALO_H + p.tap_dh[0], w0 = wt * HALO_W + p.tap_dw[0];   // tap 0 is (dh, dw) = (-ph, -pw)
         for (int dt = 0; dt < kt; ++dt) {
           const int ct = tt * p.st + p.tap_dt[dt * 9];
           for (int cb = 0; cb < num_cb; ++cb) {
             mbar_wait(aempty_bar(as), aphase ^ 1u);
-            mbar_arrive_expect_tx(afull_bar(as), HALO_TX_BYTES);
-            tma_load_4d(smem_a(as), &maps.a[0], afull_bar(as), cb * CONV_BK, w0, h0, ct);
+            if constexpr (kCG == 1) {
+              mbar_arrive_expect_tx(afull_bar(as), HALO_TX_BYTES);
+              tma_load_4d(smem_a(as), &maps.a[0], afull_bar(as), cb * CONV_BK, w0, h0, ct);
+            } else {
+              // pair: each CTA streams its own halo, all bytes are accounted on the leader's barrier
+              if (leader) mbar_arrive_expect_tx(afull_bar(as), 2 * HALO_TX_BYTES);
+              tma_load_4d_cg2(smem_a(as), &maps.a[0], mapa(afull_bar(as), 0), cb * CONV_BK, w0, h0, ct);
+            }
             if (++as == HALO_A_STAGES) { as = 0; aphase ^= 1u; }
             for (int dh = 0; dh < 3; ++dh) {
               mbar_wait(bempty_bar(bs), bphase ^ 1u);
-              mbar_arrive_expect_tx(bfull_bar(bs), b_bytes);
+              if constexpr (kCG == 1) {
+                mbar_arrive_expect_tx(bfull_bar(bs), b_bytes);
 #pragma unroll
-              for (int dw = 0; dw < 3; ++dw)
-                tma_load_2d(smem_b(bs) + dw * b_tap_bytes, &maps.b, bfull_bar(bs),
-                            (dt * 9 + dh * 3 + dw) * p.Cin + cb * CONV_BK, 0);
+                for (int dw = 0; dw < 3; ++dw)
+                  tma_load_2d(smem_b(bs) + dw * b_tap_bytes, &maps.b, bfull_bar(bs),
+                              (dt * 9 + dh * 3 + dw) * p.Cin + cb * CONV_BK, 0);
+              } else {
+                if (leader) mbar_arrive_expect_tx(bfull_bar(bs), 2 * b_bytes);
+                const uint32_t lead_bar = mapa(bfull_bar(bs), 0);
+#pragma unroll
+                for (int dw = 0; dw < 3; ++dw)
+                  tma_load_2d_cg2(smem_b(bs) + dw * b_tap_bytes, &maps.b, lead_bar,
+                                  (dt * 9 + dh * 3 + dw) * p.Cin + cb * CONV_BK, (int)(cta_rank * b_rows));
+              }
               if (++bs == p.stages) { bs = 0; bphase ^= 1u; }
             }
           }
@@ -449,14 +473,14 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     // registers); one elected lane issues the MMAs and commits.  At N = 96 an MMA lasts 56 cycles, so the issue path
     // per MMA has to stay well below that: taps and k-steps are fully unrolled, descriptors differ in their low word
     // only (start address >> 4) and are built by adding constants.
-    {
-      const uint32_t idesc = idesc_bf16(CONV_BM, (uint32_t)p.BN, 0, 0);
+    if (kCG == 1 || leader) {
+      const uint32_t idesc = idesc_bf16(CONV_BM * kCG, (uint32_t)p.BN, 0, 0);
       constexpr uint64_t b_dbase = smem_desc_base(/*sbo=*/1024, /*lbo=*/16);
       constexpr uint64_t a_dbase = smem_desc_base(/*sbo=*/(HALO_W + 2) * 128, /*lbo=*/16);
       int as = 0; uint32_t aphase = 0;
       int bs = 0; uint32_t bphase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
@@ -488,7 +512,7 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
                     for (int mh = 0; mh < 2; ++mh) {
 #pragma unroll
                       for (int k = 0; k < NK; ++k)
-                        umma_ss_lohi(d_tmem + mh * 128, a_lo + dw * kRowUnits + mh * kHalf + k * 2, a_hi,
+                        umma_ss_lohi<kCG>(d_tmem + mh * 128, a_lo + dw * kRowUnits + mh * kHalf + k * 2, a_hi,
                                      b_lo + dw * b_tap_units + k * 2, b_hi, idesc, (dw == 0 && k == 0) ? accum : 1u);
                     }
                   }
@@ -499,18 +523,18 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
                   case 2: issue(std::integral_constant<int, 2>{}); break;
                   default: issue(std::integral_constant<int, 1>{}); break;
                 }
-                tc_commit(bempty_bar(bs));
+                tc_commit_group<kCG>(bempty_bar(bs));
               }
               __syncwarp();
               accum = 1u;
               if (++bs == p.stages) { bs = 0; bphase ^= 1u; }
             }
-            if (elect_one()) tc_commit(aempty_bar(as));
+            if (elect_one()) tc_commit_group<kCG>(aempty_bar(as));
             __syncwarp();
             if (++as == HALO_A_STAGES) { as = 0; aphase ^= 1u; }
           }
         }
-        if (elect_one()) tc_commit(tfull_bar(acc));
+        if (elect_one()) tc_commit_group<kCG>(tfull_bar(acc));
         __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
@@ -524,10 +548,10 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     const long long frame = (long long)p.Ho * p.Wo;
     uint8_t* stg = smem_raw + (stg_base - smem_u32(smem_raw)) + ew * CONV_STG_BYTES;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       const int tt = t / tiles_per_frame;
       const int rem = t - tt * tiles_per_frame;
-      const int ht = rem / p.nWt, wt = rem - ht * p.nWt;
+      const int ht = rem / units_per_row, wt = (rem - ht * units_per_row) * kCG + (int)cta_rank;
       const int hbase = ht * HALO_H + mh * 16 + q * 4;       // tile row of this warp's row 0
       const int w0 = wt * HALO_W;
       // own row (TMEM lane) and the four rows this lane serves in the coalesced phase
@@ -546,16 +570,17 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * 256 + mh * 128;
-      conv_epilogue_rows<NCH>(p, t_addr, 0, stg, lane, frame, pos_own, ok_own, pos_co, ok_co, tempty_bar(acc));
+      conv_epilogue_rows<NCH, kCG == 2>(p, t_addr, 0, stg, lane, frame, pos_own, ok_own, pos_co, ok_co,
+                                        kCG == 2 ? mapa(tempty_bar(acc), 0) : tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, 512);
+    tmem_dealloc<kCG>(tmem_base, 512);
   }
 }
 
@@ -568,13 +593,34 @@ static int launch_taps(const ConvMaps& maps, const ConvParams& p, int smem, int 
   return (int)cudaGetLastError();
 }
 
-template <int NCH>
-static int launch_halo(const ConvMaps& maps, const ConvParams& p, int smem, int grid, cudaStream_t s) {
-  auto kern = gf_conv3d_halo_kernel<NCH>;
+template <int NCH, int kCG>
+static int launch_halo(const ConvMaps& maps, const ConvParams& p, int smem, int clusters, cudaStream_t s) {
+  auto kern = gf_conv3d_halo_kernel<NCH, kCG>;
   static bool configured[64] = {};
   if (int e = gf_set_smem_once(configured, reinterpret_cast<const void*>(kern), 227 * 1024)) return e;
-  kern<<<grid, HALO_THREADS, smem, s>>>(maps, p);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * kCG);
+  cfg.blockDim = dim3(HALO_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, kern, maps, p);
+}
+
+template <int kCG>
+static int dispatch_halo(const ConvMaps& maps, const ConvParams& p, int smem, int clusters, cudaStream_t s) {
+  switch (p.BN / 32) {
+    case 1: return launch_halo<1, kCG>(maps, p, smem, clusters, s);
+    case 2: return launch_halo<2, kCG>(maps, p, smem, clusters, s);
+    case 3: return launch_halo<3, kCG>(maps, p, smem, clusters, s);
+    default: return launch_halo<4, kCG>(maps, p, smem, clusters, s);
+  }
 }
 
 static inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -654,8 +700,12 @@ extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int 
     p.bw_shift = 3;
     p.nWt = (Wo + HALO_W - 1) / HALO_W;
     p.nHt = (Ho + HALO_H - 1) / HALO_H;
+    // pair form (cta_group::2): two adjacent tiles per CTA pair, M = 256 MMAs, each CTA stages half of the weight
+    // rows -- per MMA the SM then reads 5.5 KB instead of 7 KB of operands and receives half of the weight bytes, and
+    // shared-memory bandwidth (operand reads + TMA fill) is what bounds this kernel
+    const int cg = (tune.conv_impl == 2 || p.nWt < 2) ? 1 : 2;
     const int fixed = HALO_A_STAGES * HALO_STAGE_BYTES + 8 * CONV_STG_BYTES + 1024 + 512;
-    p.stages = (224 * 1024 - fixed) / (3 * p.BN * 128);       // B stages of one window row (3 taps) each
+    p.stages = (224 * 1024 - fixed) / (3 * (p.BN / cg) * 128);       // B stages of one window row (3 taps) each
     if (p.stages > HALO_MAX_B_STAGES) p.stages = HALO_MAX_B_STAGES;
     ConvMaps hm;
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)T};
@@ -665,20 +715,15 @@ extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int 
     if (hrc) return hrc;
     for (int i = 1; i < 4; ++i) hm.a[i] = hm.a[0];
     hrc = gf_make_tmap_2d_bf16(&hm.b, Wt, (uint64_t)p.ntaps * Cin, (uint64_t)Cout, (uint64_t)p.ntaps * Cin, CONV_BK,
-                               (uint32_t)p.BN);
+                               (uint32_t)(p.BN / cg));
     if (hrc) return hrc;
-    const int hsmem = fixed + p.stages * 3 * p.BN * 128;
-    const long long htiles = (long long)To * p.nWt * p.nHt;
-    int hgrid = gf_num_sms();
-    if (hgrid <= 0) return GF_ERR_NO_DRIVER;
-    if (hgrid > htiles) hgrid = (int)htiles;
+    const int hsmem = fixed + p.stages * 3 * (p.BN / cg) * 128;
+    const long long units = (long long)To * p.nHt * ((p.nWt + cg - 1) / cg);
+    int clusters = gf_num_sms() / cg;
+    if (clusters <= 0) return GF_ERR_NO_DRIVER;
+    if (clusters > units) clusters = (int)units;
     cudaStream_t hs = reinterpret_cast<cudaStream_t>(stream);
-    switch (p.BN / 32) {
-      case 1: return launch_halo<1>(hm, p, hsmem, hgrid, hs);
-      case 2: return launch_halo<2>(hm, p, hsmem, hgrid, hs);
-      case 3: return launch_halo<3>(hm, p, hsmem, hgrid, hs);
-      default: return launch_halo<4>(hm, p, hsmem, hgrid, hs);
-    }
+    return cg == 1 ? dispatch_halo<1>(hm, p, hsmem, clusters, hs) : dispatch_halo<2>(hm, p, hsmem, clusters, hs);
   }
 
   ConvMaps maps;

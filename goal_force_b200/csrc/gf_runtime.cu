@@ -157,7 +157,7 @@ extern "C" int gf_ctx_set_gemm_raster(gf_ctx* ctx, int group_m) {
 }
 
 extern "C" int gf_ctx_set_conv(gf_ctx* ctx, int impl) {
-  if (!ctx || impl < 0 || impl > 1) return GF_ERR_BAD_ARG;
+  if (!ctx || impl < 0 || impl > 2) return GF_ERR_BAD_ARG;
   ctx->tuning.conv_impl = impl;
   return 0;
 }

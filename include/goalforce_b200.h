@@ -47,7 +47,7 @@ int gf_abi_version(void);
  * kernel for Lk <= 1024), 80 / 160 / 128 = forced (160 = CTA-pair form of 80); emu_pairs -1 = kernel default, or
  * 0/2/4/6 column pairs per 16 whose exp2 runs on the FMA pipe.  gf_ctx_set_gemm_raster: rasterisation group height in
  * m-tiles, 0 = per-shape choice.  gf_ctx_set_conv: impl 0 = per-shape choice of the convolution kernel (halo form for
- * 3x3 windows with Cout <= 128), 1 = always the tap-by-tap form.
+ * 3x3 windows with Cout <= 128, as a CTA pair), 1 = always the tap-by-tap form, 2 = halo form on single CTAs.
  * gf_ctx_stats: descriptor-cache counters (any pointer may be NULL). */
 typedef struct gf_ctx gf_ctx;
 int gf_ctx_create(gf_ctx** ctx);

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--shapes", default="s3,s2,s1,s0,up2,up1,tile_s3,head,enc1")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--fused", action="store_true", help="residual + fused next-layer norm epilogue (Cout <= 256)")
+    ap.add_argument("--epi", default="", help="plain | norm (Y2 only) | res (R + Y) | resnorm (R + Y + Y2); overrides --fused")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     from goal_force_b200 import capi
@@ -41,15 +42,19 @@ def main():
         cs = (cout + 7) // 8 * 8
         b = torch.zeros(cs, dtype=torch.bfloat16, device="cuda")
         ncthw = cout < 8
-        fused = a.fused and cout <= 256 and not ncthw
-        gamma = torch.ones(cs, dtype=torch.bfloat16, device="cuda") if fused else None
-        resid = torch.randn(T, H, W, cs, device="cuda").to(torch.bfloat16) if fused else None
-        y = torch.empty((cout, T, H, W) if ncthw else (T, H, W, cs), dtype=torch.bfloat16, device="cuda")
-        yn = torch.empty((T, H, W, cs), dtype=torch.bfloat16, device="cuda") if fused else None
+        epi = a.epi or ("resnorm" if a.fused else "plain")
+        if cout > 256 or ncthw:
+            epi = "plain"
+        fused = epi != "plain"
+        want_norm, want_res, want_raw = epi in ("norm", "resnorm"), epi in ("res", "resnorm"), epi != "norm"
+        gamma = torch.ones(cs, dtype=torch.bfloat16, device="cuda") if want_norm else None
+        resid = torch.randn(T, H, W, cs, device="cuda").to(torch.bfloat16) if want_res else None
+        y = torch.empty((cout, T, H, W) if ncthw else (T, H, W, cs), dtype=torch.bfloat16, device="cuda") if want_raw else None
+        yn = torch.empty((T, H, W, cs), dtype=torch.bfloat16, device="cuda") if want_norm else None
 
         def run():
             capi.conv3d_cl(x, w, b, kernel=kernel, pad=pad, out=y, residual=resid, norm_out=yn, gamma=gamma, cout=cout,
-                           ncthw=ncthw)
+                           ncthw=ncthw, want_raw=want_raw)
         run()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -61,7 +66,7 @@ def main():
         ms = e0.elapsed_time(e1) / max(a.iters, 1)
         flops = 2.0 * T * H * W * cout * taps * cin
         res[name] = {"ms": round(ms, 3), "tflops": round(flops / ms / 1e9, 1), "gflop": round(flops / 1e9, 1),
-                     "fused": fused}
+                     "epi": epi}
         print(name, res[name], flush=True)
         del x, y, yn, resid
         torch.cuda.empty_cache()
