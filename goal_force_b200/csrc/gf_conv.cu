@@ -52,6 +52,7 @@ struct ConvParams {
   int nWt, nHt;
   int BN, num_n_tiles;
   int stages;
+  int a_stages;         // halo form: input-halo stages
   int ncthw;            // 1: Y is (Cout, To, Ho, Wo)
   int silu;
   signed char tap_map[CONV_MAX_TAPS], tap_dt[CONV_MAX_TAPS], tap_dh[CONV_MAX_TAPS], tap_dw[CONV_MAX_TAPS];
@@ -360,17 +361,29 @@ gf_conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
 // 320 threads: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter, one per accumulator).
 // The epilogue keeps the bf16 row in registers (Cout <= 128), frees the accumulator as soon as it has been read, and
 // moves R / Y / Y2 through a per-warp staging tile so that global accesses are 64-byte row segments.
-constexpr int HALO_THREADS = 320;
-constexpr int HALO_W = 8, HALO_H = 32;                   // output positions per CTA tile
-constexpr int HALO_ROWS = (HALO_W + 2) * (HALO_H + 2);   // 340
-constexpr int HALO_TX_BYTES = HALO_ROWS * 128;           // 43,520
-constexpr int HALO_STAGE_BYTES = 44 * 1024;
-constexpr int HALO_A_STAGES = 2;
+constexpr int HALO_W = 8;                                // tile width in positions (= rows of a UMMA core matrix)
+constexpr int HALO_MAX_A_STAGES = 4;
 constexpr int HALO_MAX_B_STAGES = 6;
 
-template <int NCH, int kCG>
-__global__ void __launch_bounds__(HALO_THREADS, 1)
+// MH = accumulators (16-row halves) per CTA: 2 for Cout <= 128 (two 128-column accumulators per TMEM stage), 1 for
+// wider outputs (one accumulator of up to 256 columns per stage; Cout = 384 runs as two 192-column n-tiles).
+template <int MH> struct HaloCfg {
+  static constexpr int kTileH = 16 * MH;                                   // output rows per CTA tile
+  static constexpr int kRows = (HALO_W + 2) * (kTileH + 2);                // 340 / 180 halo positions
+  static constexpr int kTxBytes = kRows * 128;                             // 43,520 / 23,040
+  static constexpr int kStageBytes = (kTxBytes + 1023) / 1024 * 1024;      // 44 KB / 23 KB
+  static constexpr int kEpiWarps = 4 * MH;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;                     // 320 / 192
+};
+
+template <int NCH, int kCG, int MH>
+__global__ void __launch_bounds__(HaloCfg<MH>::kThreads, 1)
 gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
+  using Cfg = HaloCfg<MH>;
+  constexpr int HALO_H = Cfg::kTileH;
+  constexpr int HALO_TX_BYTES = Cfg::kTxBytes;
+  constexpr int HALO_STAGE_BYTES = Cfg::kStageBytes;
+  const int HALO_A_STAGES = p.a_stages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_rows = (uint32_t)p.BN / kCG;            // weight rows staged by this CTA (pair: half of them each)
@@ -378,7 +391,7 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
   const uint32_t b_bytes = 3u * b_tap_bytes;               // a B stage holds one window row (dw = 0, 1, 2)
   const uint32_t b_base = smem_base + HALO_A_STAGES * HALO_STAGE_BYTES;
   const uint32_t stg_base = b_base + p.stages * b_bytes;
-  const uint32_t bar_base = stg_base + 8 * CONV_STG_BYTES;
+  const uint32_t bar_base = stg_base + Cfg::kEpiWarps * CONV_STG_BYTES;
   auto afull_bar = [&](int s) { return bar_base + 8u * s; };
   auto aempty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
   auto bfull_bar = [&](int s) { return bar_base + 8u * (8 + s); };
@@ -397,7 +410,7 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
   // out-of-range positions (zero-filled loads, masked stores)
   const int units_per_row = (p.nWt + kCG - 1) / kCG;
   const int tiles_per_frame = units_per_row * p.nHt;
-  const int num_tiles = p.To * tiles_per_frame;
+  const int num_tiles = p.To * tiles_per_frame * p.num_n_tiles;       // n-tile innermost: neighbours share the halo in L2
   const int num_cb = (p.Cin + CONV_BK - 1) / CONV_BK;
   const int kt = p.ntaps / 9;
 
@@ -409,7 +422,7 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     if (elect_one()) {
       for (int s = 0; s < HALO_A_STAGES; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
       for (int s = 0; s < p.stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8 * kCG); }
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::kEpiWarps * kCG); }
       fence_mbar_init();
     }
     __syncwarp();
@@ -428,8 +441,9 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
       int as = 0; uint32_t aphase = 0;
       int bs = 0; uint32_t bphase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int tt = t / tiles_per_frame;
-        const int rem = t - tt * tiles_per_frame;
+        const int mu = t / p.num_n_tiles, n0 = (t - mu * p.num_n_tiles) * p.BN;
+        const int tt = mu / tiles_per_frame;
+        const int rem = mu - tt * tiles_per_frame;
         const int ht = rem / units_per_row, wt = (rem - ht * units_per_row) * kCG + (int)cta_rank;
         const int h0 = ht * HALO_H + p.tap_dh[0], w0 = wt * HALO_W + p.tap_dw[0];   // tap 0 is (dh, dw) = (-ph, -pw)
         for (int dt = 0; dt < kt; ++dt) {
@@ -452,14 +466,14 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
 #pragma unroll
                 for (int dw = 0; dw < 3; ++dw)
                   tma_load_2d(smem_b(bs) + dw * b_tap_bytes, &maps.b, bfull_bar(bs),
-                              (dt * 9 + dh * 3 + dw) * p.Cin + cb * CONV_BK, 0);
+                              (dt * 9 + dh * 3 + dw) * p.Cin + cb * CONV_BK, n0);
               } else {
                 if (leader) mbar_arrive_expect_tx(bfull_bar(bs), 2 * b_bytes);
                 const uint32_t lead_bar = mapa(bfull_bar(bs), 0);
 #pragma unroll
                 for (int dw = 0; dw < 3; ++dw)
                   tma_load_2d_cg2(smem_b(bs) + dw * b_tap_bytes, &maps.b, lead_bar,
-                                  (dt * 9 + dh * 3 + dw) * p.Cin + cb * CONV_BK, (int)(cta_rank * b_rows));
+                                  (dt * 9 + dh * 3 + dw) * p.Cin + cb * CONV_BK, n0 + (int)(cta_rank * b_rows));
               }
               if (++bs == p.stages) { bs = 0; bphase ^= 1u; }
             }
@@ -503,13 +517,13 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
               const uint32_t a_lo = a_lo0 + (uint32_t)(dh * (HALO_W + 2) * kRowUnits);
               const uint32_t b_tap_units = b_tap_bytes >> 4;
               if (elect_one()) {
-                // one window row: 3 taps x 2 accumulators x nk k-steps, straight-line for every nk
+                // one window row: 3 taps x MH accumulators x nk k-steps, straight-line for every nk
                 auto issue = [&](auto nk_c) {
                   constexpr int NK = decltype(nk_c)::value;
 #pragma unroll
                   for (int dw = 0; dw < 3; ++dw) {
 #pragma unroll
-                    for (int mh = 0; mh < 2; ++mh) {
+                    for (int mh = 0; mh < MH; ++mh) {
 #pragma unroll
                       for (int k = 0; k < NK; ++k)
                         umma_ss_lohi<kCG>(d_tmem + mh * 128, a_lo + dw * kRowUnits + mh * kHalf + k * 2, a_hi,
@@ -542,15 +556,16 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
   } else {
     // ===================================================== epilogue (warps 2..9)
     const int ew = warp - 2;
-    const int mh = ew >> 2;                     // accumulator (upper / lower 16 tile rows)
+    const int mh = ew >> 2;                     // accumulator (upper / lower 16 tile rows; always 0 for MH = 1)
     const int q = warp & 3;                     // TMEM lane quarter
     const int lane = (int)lane_id();
     const long long frame = (long long)p.Ho * p.Wo;
     uint8_t* stg = smem_raw + (stg_base - smem_u32(smem_raw)) + ew * CONV_STG_BYTES;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      const int tt = t / tiles_per_frame;
-      const int rem = t - tt * tiles_per_frame;
+      const int mu = t / p.num_n_tiles, n0 = (t - mu * p.num_n_tiles) * p.BN;
+      const int tt = mu / tiles_per_frame;
+      const int rem = mu - tt * tiles_per_frame;
       const int ht = rem / units_per_row, wt = (rem - ht * units_per_row) * kCG + (int)cta_rank;
       const int hbase = ht * HALO_H + mh * 16 + q * 4;       // tile row of this warp's row 0
       const int w0 = wt * HALO_W;
@@ -570,7 +585,7 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * 256 + mh * 128;
-      conv_epilogue_rows<NCH, kCG == 2>(p, t_addr, 0, stg, lane, frame, pos_own, ok_own, pos_co, ok_co,
+      conv_epilogue_rows<NCH, kCG == 2>(p, t_addr, n0, stg, lane, frame, pos_own, ok_own, pos_co, ok_co,
                                         kCG == 2 ? mapa(tempty_bar(acc), 0) : tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -593,14 +608,14 @@ static int launch_taps(const ConvMaps& maps, const ConvParams& p, int smem, int 
   return (int)cudaGetLastError();
 }
 
-template <int NCH, int kCG>
+template <int NCH, int kCG, int MH>
 static int launch_halo(const ConvMaps& maps, const ConvParams& p, int smem, int clusters, cudaStream_t s) {
-  auto kern = gf_conv3d_halo_kernel<NCH, kCG>;
+  auto kern = gf_conv3d_halo_kernel<NCH, kCG, MH>;
   static bool configured[64] = {};
   if (int e = gf_set_smem_once(configured, reinterpret_cast<const void*>(kern), 227 * 1024)) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * kCG);
-  cfg.blockDim = dim3(HALO_THREADS);
+  cfg.blockDim = dim3(HaloCfg<MH>::kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -616,11 +631,16 @@ static int launch_halo(const ConvMaps& maps, const ConvParams& p, int smem, int 
 template <int kCG>
 static int dispatch_halo(const ConvMaps& maps, const ConvParams& p, int smem, int clusters, cudaStream_t s) {
   switch (p.BN / 32) {
-    case 1: return launch_halo<1, kCG>(maps, p, smem, clusters, s);
-    case 2: return launch_halo<2, kCG>(maps, p, smem, clusters, s);
-    case 3: return launch_halo<3, kCG>(maps, p, smem, clusters, s);
-    default: return launch_halo<4, kCG>(maps, p, smem, clusters, s);
+    case 1: return launch_halo<1, kCG, 2>(maps, p, smem, clusters, s);
+    case 2: return launch_halo<2, kCG, 2>(maps, p, smem, clusters, s);
+    case 3: return launch_halo<3, kCG, 2>(maps, p, smem, clusters, s);
+    default: return launch_halo<4, kCG, 2>(maps, p, smem, clusters, s);
   }
+}
+
+// wide outputs (128 < BN <= 256): one accumulator per CTA, always as a CTA pair
+static int dispatch_halo_wide(const ConvMaps& maps, const ConvParams& p, int smem, int clusters, cudaStream_t s) {
+  return p.BN <= 192 ? launch_halo<6, 2, 1>(maps, p, smem, clusters, s) : launch_halo<8, 2, 1>(maps, p, smem, clusters, s);
 }
 
 static inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -692,37 +712,51 @@ extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int 
       }
 
   const CtxTuning tune = gf_ctx_tuning(ctx);
-  const bool halo = kh == 3 && kw == 3 && sh == 1 && st == 1 && cout32 <= 128 && tune.conv_impl != 1;
-  if (halo) {
-    // 32 x 8 output positions per CTA, one 34 x 10 input halo per (dt, channel block); see gf_conv3d_halo_kernel
-    p.num_n_tiles = 1;
-    p.BN = cout32;
+  const bool halo_ok = kh == 3 && kw == 3 && sh == 1 && st == 1 && tune.conv_impl != 1;
+  const bool wide = cout32 > 128;                       // one accumulator per CTA, pair only
+  if (halo_ok && (!wide || (Wo > HALO_W && tune.conv_impl != 2))) {
+    // narrow: 32 x 8 output positions per CTA (two accumulators); wide: 16 x 8 (one accumulator of <= 256 columns, Cout
+    // split evenly into n-tiles).  One input halo per (dt, channel block); see gf_conv3d_halo_kernel.
+    const int MH = wide ? 1 : 2;
+    if (wide) {
+      p.num_n_tiles = (cout32 + 255) / 256;
+      p.BN = (((cout32 + p.num_n_tiles - 1) / p.num_n_tiles) + 31) & ~31;
+      if (Y2 && p.num_n_tiles != 1) return GF_ERR_UNSUPPORTED;
+    } else {
+      p.num_n_tiles = 1;
+      p.BN = cout32;
+    }
     p.bw_shift = 3;
     p.nWt = (Wo + HALO_W - 1) / HALO_W;
-    p.nHt = (Ho + HALO_H - 1) / HALO_H;
+    p.nHt = (Ho + 16 * MH - 1) / (16 * MH);
     // pair form (cta_group::2): two adjacent tiles per CTA pair, M = 256 MMAs, each CTA stages half of the weight
-    // rows -- per MMA the SM then reads 5.5 KB instead of 7 KB of operands and receives half of the weight bytes, and
-    // shared-memory bandwidth (operand reads + TMA fill) is what bounds this kernel
-    const int cg = (tune.conv_impl == 2 || p.nWt < 2) ? 1 : 2;
-    const int fixed = HALO_A_STAGES * HALO_STAGE_BYTES + 8 * CONV_STG_BYTES + 1024 + 512;
-    p.stages = (224 * 1024 - fixed) / (3 * (p.BN / cg) * 128);       // B stages of one window row (3 taps) each
+    // rows.  Shared-memory bandwidth (128 B/clk for operand reads AND the TMA fill) is what bounds these kernels: at
+    // N = 96 a single CTA moves 7 KB + 2.8 KB per MMA (76 cycles measured against 48 of math), the pair 5.5 + 1.8 KB.
+    const int cg = (!wide && (tune.conv_impl == 2 || p.nWt < 2)) ? 1 : 2;
+    const int a_stage_bytes = wide ? HaloCfg<1>::kStageBytes : HaloCfg<2>::kStageBytes;
+    const int b_stage_bytes = 3 * (p.BN / cg) * 128;                  // one window row (3 taps) of this CTA's weight rows
+    p.a_stages = wide ? 3 : 2;
+    const int fixed = p.a_stages * a_stage_bytes + 4 * MH * CONV_STG_BYTES + 1024 + 512;
+    p.stages = (224 * 1024 - fixed) / b_stage_bytes;
     if (p.stages > HALO_MAX_B_STAGES) p.stages = HALO_MAX_B_STAGES;
+    if (p.stages < 2) return GF_ERR_UNSUPPORTED;
     ConvMaps hm;
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)T};
     const uint64_t strides[3] = {(uint64_t)ldx * 2, (uint64_t)ldx * 2 * W, (uint64_t)ldx * 2 * W * H};
-    const uint32_t box[4] = {(uint32_t)CONV_BK, (uint32_t)(HALO_W + 2), (uint32_t)(HALO_H + 2), 1u};
+    const uint32_t box[4] = {(uint32_t)CONV_BK, (uint32_t)(HALO_W + 2), (uint32_t)(16 * MH + 2), 1u};
     int hrc = gf_make_tmap_4d_bf16(&hm.a[0], X, dims, strides, box);
     if (hrc) return hrc;
     for (int i = 1; i < 4; ++i) hm.a[i] = hm.a[0];
     hrc = gf_make_tmap_2d_bf16(&hm.b, Wt, (uint64_t)p.ntaps * Cin, (uint64_t)Cout, (uint64_t)p.ntaps * Cin, CONV_BK,
                                (uint32_t)(p.BN / cg));
     if (hrc) return hrc;
-    const int hsmem = fixed + p.stages * 3 * (p.BN / cg) * 128;
-    const long long units = (long long)To * p.nHt * ((p.nWt + cg - 1) / cg);
+    const int hsmem = fixed + p.stages * b_stage_bytes;
+    const long long units = (long long)To * p.nHt * ((p.nWt + cg - 1) / cg) * p.num_n_tiles;
     int clusters = gf_num_sms() / cg;
     if (clusters <= 0) return GF_ERR_NO_DRIVER;
     if (clusters > units) clusters = (int)units;
     cudaStream_t hs = reinterpret_cast<cudaStream_t>(stream);
+    if (wide) return dispatch_halo_wide(hm, p, hsmem, clusters, hs);
     return cg == 1 ? dispatch_halo<1>(hm, p, hsmem, clusters, hs) : dispatch_halo<2>(hm, p, hsmem, clusters, hs);
   }
 
