@@ -20,10 +20,14 @@ static inline int stream_grid(long long items, int threads) {
 // ---------------------------------------------------------------------------------------------------- RMS_norm (+SiLU)
 // RMS_norm.forward (:55-70): F.normalize(x, dim=channel) * sqrt(C) * gamma, then nn.SiLU in ResidualBlock / head.
 // G lanes share one row (G = power of two <= 32, G * 8 * kMaxVec >= C); 32 / G rows per warp.
+// NV = 16-byte vectors per lane, U = independent row groups a warp keeps in flight per iteration: with one 16-byte
+// load per lane outstanding the kernel sat at 2.4 TB/s (latency-bound: 32 warps x 384 B per SM in flight); U x NV = 4
+// loads per lane are issued before the first reduction.
 constexpr int VAE_NORM_MAXVEC = 4;
-__global__ void vae_rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
-                                   long long ldy, long long rows, int C, const __nv_bfloat16* __restrict__ gamma,
-                                   int silu, int g_shift) {
+template <int NV, int U>
+__global__ void __launch_bounds__(256)
+vae_rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
+                   long long rows, int C, const __nv_bfloat16* __restrict__ gamma, int silu, int g_shift) {
   const int G = 1 << g_shift;
   const int rows_per_warp = 32 >> g_shift;
   const int lane = threadIdx.x & 31;
@@ -32,41 +36,55 @@ __global__ void vae_rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long lon
   const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long num_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const float sqrt_c = sqrtf((float)C);
-  for (long long base = warp_global * rows_per_warp; base < rows; base += num_warps * rows_per_warp) {
-    const long long row = base + (lane >> g_shift);
-    const bool ok = row < rows;
-    uint4 v[VAE_NORM_MAXVEC];
-    float ss = 0.0f;
+  uint4 gv[NV];
 #pragma unroll
-    for (int i = 0; i < VAE_NORM_MAXVEC; ++i) {
-      const int vi = sub + i * G;
-      v[i] = make_uint4(0, 0, 0, 0);
-      if (ok && vi < nvec) v[i] = *reinterpret_cast<const uint4*>(x + row * ldx + vi * 8);
-      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+  for (int i = 0; i < NV; ++i) {
+    const int vi = sub + i * G;
+    gv[i] = vi < nvec ? __ldg(reinterpret_cast<const uint4*>(gamma + vi * 8)) : make_uint4(0, 0, 0, 0);
+  }
+  for (long long base = warp_global * rows_per_warp * U; base < rows; base += num_warps * rows_per_warp * U) {
+    uint4 v[U][NV];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ss += bf16_lo(w[j]) * bf16_lo(w[j]) + bf16_hi(w[j]) * bf16_hi(w[j]);
+    for (int u = 0; u < U; ++u) {
+      const long long row = base + u * rows_per_warp + (lane >> g_shift);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = sub + i * G;
+        v[u][i] = make_uint4(0, 0, 0, 0);
+        if (row < rows && vi < nvec) v[u][i] = *reinterpret_cast<const uint4*>(x + row * ldx + vi * 8);
+      }
     }
-    for (int o = G >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float rinv = sqrt_c / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
-    for (int i = 0; i < VAE_NORM_MAXVEC; ++i) {
-      const int vi = sub + i * G;
-      if (ok && vi < nvec) {
-        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + vi * 8));
-        const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-        const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-        uint32_t o[4];
+    for (int u = 0; u < U; ++u) {
+      const long long row = base + u * rows_per_warp + (lane >> g_shift);
+      float ss = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float a = bf16_lo(w[j]) * rinv * bf16_lo(gw[j]);
-          float b = bf16_hi(w[j]) * rinv * bf16_hi(gw[j]);
-          if (silu) {
-            a = silu_fast(a);
-            b = silu_fast(b);
+      for (int i = 0; i < NV; ++i) {
+        const uint32_t w[4] = {v[u][i].x, v[u][i].y, v[u][i].z, v[u][i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ss += bf16_lo(w[j]) * bf16_lo(w[j]) + bf16_hi(w[j]) * bf16_hi(w[j]);
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rinv = sqrt_c / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = sub + i * G;
+        if (row < rows && vi < nvec) {
+          const uint32_t w[4] = {v[u][i].x, v[u][i].y, v[u][i].z, v[u][i].w};
+          const uint32_t gw[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float a = bf16_lo(w[j]) * rinv * bf16_lo(gw[j]);
+            float b = bf16_hi(w[j]) * rinv * bf16_hi(gw[j]);
+            if (silu) {
+              a = silu_fast(a);
+              b = silu_fast(b);
+            }
+            o[j] = pack_bf16x2(a, b);
           }
-          o[j] = pack_bf16x2(a, b);
+          *reinterpret_cast<uint4*>(y + row * ldy + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        *reinterpret_cast<uint4*>(y + row * ldy + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
   }
@@ -242,11 +260,18 @@ extern "C" int gf_vae_rmsnorm_bf16(const void* x, long long ldx, void* y, long l
   int g_shift = 0;
   while ((1 << g_shift) < nvec && g_shift < 5) ++g_shift;
   const int rows_per_warp = 32 >> g_shift;
-  const long long warps = (rows + rows_per_warp - 1) / rows_per_warp;
+  const int nv = (nvec + (1 << g_shift) - 1) >> g_shift;            // vectors per lane: 1 (C <= 256), 2 (<= 512), 4
+  const int unroll = nv == 1 ? 4 : (nv == 2 ? 2 : 1);
+  const long long warps = (rows + (long long)rows_per_warp * unroll - 1) / ((long long)rows_per_warp * unroll);
   const int threads = 256;
-  vae_rmsnorm_kernel<<<stream_grid(warps * 32, threads), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, rows, C,
-      reinterpret_cast<const __nv_bfloat16*>(gamma), silu, g_shift);
+  const int grid = stream_grid(warps * 32, threads);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(gamma);
+  if (nv == 1) vae_rmsnorm_kernel<1, 4><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, rows, C, gp, silu, g_shift);
+  else if (nv == 2) vae_rmsnorm_kernel<2, 2><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, rows, C, gp, silu, g_shift);
+  else vae_rmsnorm_kernel<4, 1><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, rows, C, gp, silu, g_shift);
   return (int)cudaGetLastError();
 }
 

@@ -117,12 +117,10 @@ class WanVideoVAEB200:
         """next_norm: (gamma, silu) of the consumer's RMS_norm.  Returns (raw or None, normed or None)."""
         cv = self.conv[name]
         cout = cv.cout if cout is None else cout
-        # Fusing the consumer's RMS_norm pays under a full 27-tap window, where the longer epilogue hides behind the
-        # MMAs of the next tile.  The 9-tap resample convolutions have a third of the MMA time per tile: there the
-        # fused epilogue becomes the critical path and costs more than the separate norm kernel (measured with
-        # tools/conv_bench.py --fused: 192->96 at 81x480x832 8.6 ms + 2.3 ms unfused vs 12.3 ms fused).
-        kt, kh, kw = cv.kernel
-        fuse = next_norm is not None and cout <= FUSE_MAX_CHANNELS and not ncthw and kt * kh * kw >= 27
+        # The consumer's RMS_norm + SiLU is fused whenever the channel row fits one tile: measured on the final kernels
+        # (tools/conv_bench.py --epi rawnorm) it adds 1.3 ms to the 192 -> 96 resample convolution at 81 x 480 x 832 and
+        # 0.3 ms to 384 -> 192, against 2-5 ms for a separate pass over the same tensor.
+        fuse = next_norm is not None and cout <= FUSE_MAX_CHANNELS and not ncthw
         w = cv.w if cout == cv.cout else cv.w[:cout]
         y, yn = capi.conv3d_cl(x, w, cv.bias, kernel=cv.kernel, stride=stride, pad=pad, out_dims=out_dims, out=out,
                                residual=residual, gamma=next_norm[0] if fuse else None,
@@ -257,6 +255,7 @@ class WanVideoVAEB200:
         capi.vae_planes_to_cl(video, 8, out=padded[: T * H * (W + 2) * 8].view(T, H, W + 2, 8), wpad=1)
         windows = torch.as_strided(padded, (T, H, W + 2, 64), (H * (W + 2) * 8, (W + 2) * 8, 8, 1))
         cv = self.conv[p + "conv1"]
+        # 9 k-blocks per tile: the MMAs are too short to hide a fused epilogue here (16.6 ms fused against 7.2 + 2.7 ms)
         x, _ = capi.conv3d_cl(windows, self.conv1_folded, cv.bias, kernel=(3, 3, 1), pad=(2, 1, 0), out_dims=(T, H, W))
         xn = capi.vae_rmsnorm(x, self.gamma[seq[0][1] + ".residual.0"], silu=True)
         del padded, windows

@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--shapes", default="s3,s2,s1,s0,up2,up1,tile_s3,head,enc1")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--fused", action="store_true", help="residual + fused next-layer norm epilogue (Cout <= 256)")
-    ap.add_argument("--epi", default="", help="plain | norm (Y2 only) | res (R + Y) | resnorm (R + Y + Y2); overrides --fused")
+    ap.add_argument("--epi", default="", help="plain | norm (Y2 only) | rawnorm (Y + Y2) | res (R + Y) | resnorm (R + Y + Y2); overrides --fused")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     from goal_force_b200 import capi
@@ -46,7 +46,7 @@ def main():
         if cout > 256 or ncthw:
             epi = "plain"
         fused = epi != "plain"
-        want_norm, want_res, want_raw = epi in ("norm", "resnorm"), epi in ("res", "resnorm"), epi != "norm"
+        want_norm, want_res, want_raw = epi in ("norm", "resnorm", "rawnorm"), epi in ("res", "resnorm"), epi != "norm"
         gamma = torch.ones(cs, dtype=torch.bfloat16, device="cuda") if want_norm else None
         resid = torch.randn(T, H, W, cs, device="cuda").to(torch.bfloat16) if want_res else None
         y = torch.empty((cout, T, H, W) if ncthw else (T, H, W, cs), dtype=torch.bfloat16, device="cuda") if want_raw else None
