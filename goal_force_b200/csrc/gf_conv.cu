@@ -69,8 +69,38 @@ struct ConvParams {
 // registers, stores Y and hands the accumulator back; pass 1 (fused RMS_norm + SiLU of the next layer) works from the
 // registers.  R / Y / Y2 move through the warp's staging tile `stg` (32 rows x 80 B) so that every global access is a
 // 64-byte row segment: lane l owns row l in the math, and serves rows (l >> 2) + 8 i, 16-byte column (l & 3) in the I/O.
+constexpr int CONV_TAB_ENTRIES = 1024;                   // bias / gamma tables in shared memory (Cout <= 1024 per launch)
+constexpr int CONV_TAB_BYTES = 2 * CONV_TAB_ENTRIES * 2;
+
+// bias and gamma of the launch, zero-padded, copied once per CTA: the epilogue reads them per 32-column chunk, and a
+// global (even L1-resident) load per chunk sat on its critical path.  Called by `nthreads` threads with ids 0..
+__device__ __forceinline__ void conv_fill_tables(const ConvParams& p, __nv_bfloat16* tab, int tid, int nthreads) {
+  for (int i = tid; i < CONV_TAB_ENTRIES; i += nthreads) {
+    tab[i] = (p.bias && i < p.cout_store) ? p.bias[i] : __float2bfloat16_rn(0.0f);
+    tab[CONV_TAB_ENTRIES + i] = (p.gamma && i < p.cout_store) ? p.gamma[i] : __float2bfloat16_rn(0.0f);
+  }
+}
+
+// L2 prefetch of the residual rows of the coming tile, issued before the wait for its accumulator: the loads of the
+// epilogue then hit L2 instead of exposing a DRAM round trip per 32-column chunk.
+template <int NCH>
+__device__ __forceinline__ void conv_prefetch_residual(const ConvParams& p, int n0, int lane,
+                                                       const long long (&pos_co)[4], const bool (&ok_co)[4]) {
+  if (p.R == nullptr || (lane & 3) != 0) return;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col0 = n0 + c * 32;
+    if (c * 32 < p.BN && col0 < p.cout_store) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (ok_co[i]) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R + pos_co[i] * p.ldr + col0));
+    }
+  }
+}
+
 template <int NCH, bool kRemoteArrive = false>
-__device__ __forceinline__ void conv_epilogue_rows(const ConvParams& p, uint32_t t_addr, int n0, uint8_t* stg, int lane,
+__device__ __forceinline__ void conv_epilogue_rows(const ConvParams& p, uint32_t t_addr, int n0, uint8_t* stg,
+                                                   const __nv_bfloat16* tab, int lane,
                                                    long long frame, long long pos_own, bool ok_own,
                                                    const long long (&pos_co)[4], const bool (&ok_co)[4],
                                                    uint32_t tempty_addr) {
@@ -107,7 +137,7 @@ __device__ __forceinline__ void conv_epilogue_rows(const ConvParams& p, uint32_t
       for (int g = 0; g < 4; ++g) {
         const int cg = col0 + g * 8;
         uint4 bv = make_uint4(0, 0, 0, 0);
-        if (p.bias && cg < p.cout_store) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + cg));
+        if (cg < p.cout_store) bv = *reinterpret_cast<const uint4*>(tab + cg);
         const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -169,7 +199,7 @@ __device__ __forceinline__ void conv_epilogue_rows(const ConvParams& p, uint32_t
         for (int g = 0; g < 4; ++g) {
           const int cg = col0 + g * 8;
           uint4 gv = make_uint4(0, 0, 0, 0);
-          if (cg < p.cout_store) gv = __ldg(reinterpret_cast<const uint4*>(p.gamma + cg));
+          if (cg < p.cout_store) gv = *reinterpret_cast<const uint4*>(tab + CONV_TAB_ENTRIES + cg);
           const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
           uint32_t o[4];
 #pragma unroll
@@ -208,6 +238,7 @@ gf_conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * CONV_MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * CONV_MAX_STAGES + 2 + a); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * CONV_MAX_STAGES + 4);
+  __nv_bfloat16* tab = reinterpret_cast<__nv_bfloat16*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
   auto smem_a = [&](int s) { return smem_base + s * stage_bytes; };
   auto smem_b = [&](int s) { return smem_base + s * stage_bytes + CONV_A_BYTES; };
 
@@ -222,6 +253,7 @@ gf_conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.a[i]);
     tma_prefetch_desc(&maps.b);
   }
+  if (warp >= 2) conv_fill_tables(p, tab, (int)threadIdx.x - 64, CONV_THREADS - 64);
   if (warp == 1) {
     if (elect_one()) {
       for (int s = 0; s < p.stages; ++s) {
@@ -329,10 +361,12 @@ gf_conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         ok_co[i] = h < p.Ho && w < p.Wo;
         pos_co[i] = (long long)tt * frame + (long long)h * p.Wo + w;
       }
+      conv_prefetch_residual<NCH>(p, nt * p.BN, lane, pos_co, ok_co);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * 256;
-      conv_epilogue_rows<NCH>(p, t_addr, nt * p.BN, stg, lane, frame, pos_own, ok_own, pos_co, ok_co, tempty_bar(acc));
+      conv_epilogue_rows<NCH>(p, t_addr, nt * p.BN, stg, tab, lane, frame, pos_own, ok_own, pos_co, ok_co,
+                              tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -399,6 +433,7 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
   auto tfull_bar = [&](int a) { return bar_base + 8u * (8 + 2 * HALO_MAX_B_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (10 + 2 * HALO_MAX_B_STAGES + a); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (12 + 2 * HALO_MAX_B_STAGES);
+  __nv_bfloat16* tab = reinterpret_cast<__nv_bfloat16*>(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));
   auto smem_a = [&](int s) { return smem_base + s * HALO_STAGE_BYTES; };
   auto smem_b = [&](int s) { return b_base + s * b_bytes; };
 
@@ -418,6 +453,7 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
   }
+  if (warp >= 2) conv_fill_tables(p, tab, (int)threadIdx.x - 64, Cfg::kThreads - 64);
   if (warp == 1) {
     if (elect_one()) {
       for (int s = 0; s < HALO_A_STAGES; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
@@ -582,10 +618,11 @@ gf_conv3d_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
         ok_co[i] = h < p.Ho && w < p.Wo;
         pos_co[i] = (long long)tt * frame + (long long)h * p.Wo + w;
       }
+      conv_prefetch_residual<NCH>(p, n0, lane, pos_co, ok_co);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * 256 + mh * 128;
-      conv_epilogue_rows<NCH, kCG == 2>(p, t_addr, n0, stg, lane, frame, pos_own, ok_own, pos_co, ok_co,
+      conv_epilogue_rows<NCH, kCG == 2>(p, t_addr, n0, stg, tab, lane, frame, pos_own, ok_own, pos_co, ok_co,
                                         kCG == 2 ? mapa(tempty_bar(acc), 0) : tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -663,6 +700,7 @@ extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int 
        reinterpret_cast<uintptr_t>(gamma)) & 15)
     return GF_ERR_BAD_ARG;
   const int cout_store = (Cout + 7) & ~7;
+  if (cout_store > CONV_TAB_ENTRIES) return GF_ERR_UNSUPPORTED;
   if (!out_ncthw && Y && ((ldy % 8) || ldy < cout_store)) return GF_ERR_BAD_ARG;
   if (out_ncthw && (R || Y2 || Cout > 32)) return GF_ERR_UNSUPPORTED;
   if (R && ((ldr % 8) || ldr < cout_store)) return GF_ERR_BAD_ARG;
@@ -736,7 +774,7 @@ extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int 
     const int a_stage_bytes = wide ? HaloCfg<1>::kStageBytes : HaloCfg<2>::kStageBytes;
     const int b_stage_bytes = 3 * (p.BN / cg) * 128;                  // one window row (3 taps) of this CTA's weight rows
     p.a_stages = wide ? 3 : 2;
-    const int fixed = p.a_stages * a_stage_bytes + 4 * MH * CONV_STG_BYTES + 1024 + 512;
+    const int fixed = p.a_stages * a_stage_bytes + 4 * MH * CONV_STG_BYTES + 1024 + 512 + CONV_TAB_BYTES;
     p.stages = (224 * 1024 - fixed) / b_stage_bytes;
     if (p.stages > HALO_MAX_B_STAGES) p.stages = HALO_MAX_B_STAGES;
     if (p.stages < 2) return GF_ERR_UNSUPPORTED;
@@ -779,7 +817,7 @@ extern "C" int gf_conv3d_cl_bf16(gf_ctx* ctx, const void* X, long long ldx, int 
                             (uint32_t)p.BN);
   if (rc) return rc;
 
-  const int smem = p.stages * stage_bytes + 4 * CONV_STG_BYTES + 1024 + 256;
+  const int smem = p.stages * stage_bytes + 4 * CONV_STG_BYTES + 1024 + 256 + CONV_TAB_BYTES;
   const long long tiles = (long long)To * p.nWt * p.nHt * p.num_n_tiles;
   int grid = gf_num_sms();
   if (grid <= 0) return GF_ERR_NO_DRIVER;
