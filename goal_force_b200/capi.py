@@ -58,6 +58,7 @@ SIGNATURES = {
     "gf_softmax_f32_bf16": [_p, _ll, _p, _ll, _i, _i, _i, _f, _p],
     "gf_vae_planes_to_cl_bf16": [_p, _ll, _i, _p, _ll, _i, _p, _p, _i, _i, _i, _p],
     "gf_vae_cl_to_planes_bf16": [_p, _ll, _ll, _i, _p, _p, _p, _i, _p],
+    "gf_vae_head_gather_bf16": [_p, _ll, _p, _p, _i, _i, _i, _i, _p],
     "gf_vae_blend_bf16": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p],
     "gf_vae_blend_finish_bf16": [_p, _ll, _i, _i, _p, _i, _p],
     "gf_peer_alloc": [ctypes.POINTER(ctypes.c_void_p), _ll],
@@ -623,6 +624,16 @@ def vae_cl_to_planes(src: torch.Tensor, C: int, *, mean: torch.Tensor | None = N
         _req(mean, "mean", torch.float32); _req(inv_std, "inv_std", torch.float32)
     _call("vae_rowwise", 4.0 * T * H * W * C, load().gf_vae_cl_to_planes_bf16, src.data_ptr(), src.stride(2), T * H * W, C,
           out.data_ptr(), _ptr(mean), _ptr(inv_std), mode, _stream())
+    return out
+
+
+def vae_head_gather(D: torch.Tensor, bias: torch.Tensor, C: int) -> torch.Tensor:
+    """D: [T, H, W, >= 36] partial sums per spatial tap (channel tap*4 + co); bias fp32 [C] -> (C, T, H, W) bf16."""
+    _req(D, "D"); _req(bias, "bias", torch.float32)
+    T, H, W, _ = D.shape
+    out = torch.empty((C, T, H, W), dtype=torch.bfloat16, device=D.device)
+    _call("vae_rowwise", 2.0 * T * H * W * (D.shape[3] + C), load().gf_vae_head_gather_bf16, D.data_ptr(), D.stride(2),
+          bias.data_ptr(), out.data_ptr(), C, T, H, W, _stream())
     return out
 
 

@@ -212,6 +212,36 @@ __global__ void vae_cl_to_planes_kernel(const __nv_bfloat16* __restrict__ src, l
   }
 }
 
+// ---------------------------------------------------------------------------------------------------- 3-channel head
+// The decoder head is a 3x3x3 convolution to 3 channels (:801-803): as an implicit GEMM its N would be 3 padded to 32.
+// It runs instead as a (3,1,1) convolution whose output channels are the 9 spatial taps x (3 channels + 1 pad):
+//   D[t, h, w, tap*4 + co] = sum_{dt, ci} W[co, ci, dt, dh, dw] * X[t + dt - 2, h, w, ci],   tap = dh*3 + dw
+// and this kernel gathers  out[co, t, h, w] = bias[co] + sum_tap D[t, h + dh - 1, w + dw - 1, tap*4 + co]  (positions
+// outside the frame contribute zero: the convolution's zero padding), fp32 sum of the bf16 partials, one rounding.
+__global__ void vae_head_gather_kernel(const __nv_bfloat16* __restrict__ D, long long ld, const float* __restrict__ bias,
+                                       __nv_bfloat16* __restrict__ out, int C, int T, int H, int W) {
+  const long long plane = (long long)T * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const int h = (int)((i / W) % H);
+    const long long t = i / ((long long)W * H);
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int hh = h + dh - 1;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int ww = w + dw - 1;
+        if (ww < 0 || ww >= W) continue;
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(D + ((t * H + hh) * W + ww) * ld + (dh * 3 + dw) * 4));
+        acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+      }
+    }
+    for (int c = 0; c < C; ++c) out[c * plane + i] = __float2bfloat16_rn(acc[c] + bias[c]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------- tile blending
 // WanVideoVAE.tiled_decode / tiled_encode (:1133-1153,1184-1204): values[:, :, h0:h0+th, w0:w0+tw] += tile * mask with
 // the bf16 rounding of the reference's two torch ops (mul, then add).  tile: (C, T, th, tw); mask: [th][tw] bf16.
@@ -347,5 +377,15 @@ extern "C" int gf_vae_blend_finish_bf16(void* values, long long planes, int H, i
                                                                     clamp);
   else if (clamp)
     vae_clamp_kernel<<<stream_grid(total, 256), 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(values), total);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gf_vae_head_gather_bf16(const void* D, long long ld, const float* bias, void* out, int C, int T, int H,
+                                       int W, void* stream) {
+  if (!D || !bias || !out || C < 1 || C > 4 || T <= 0 || H <= 0 || W <= 0 || (ld % 8) || ld < 36) return GF_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(D) & 15)) return GF_ERR_BAD_ARG;
+  const long long plane = (long long)T * H * W;
+  vae_head_gather_kernel<<<stream_grid(plane, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(D), ld, bias, reinterpret_cast<__nv_bfloat16*>(out), C, T, H, W);
   return (int)cudaGetLastError();
 }

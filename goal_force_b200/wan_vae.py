@@ -103,6 +103,15 @@ class WanVideoVAEB200:
         wf = torch.zeros((cout, 3, 3, 8, 8), dtype=torch.float32, device=self.device)                 # [co, dt, dh, dw, c]
         wf[:, :, :, :3, :cin] = w.permute(0, 2, 3, 4, 1)
         self.conv1_folded = wf.reshape(cout, 9 * 64).to(torch.bfloat16).contiguous()
+        # decoder.head.2 (3x3x3 to 3 channels): N = 3 would waste the tensor core, so its nine spatial taps become output
+        # channels of a (3,1,1) convolution (channel tap*4 + co) and gf_vae_head_gather_bf16 sums them per pixel
+        w = state_dict["decoder.head.2.weight"].detach().to(device=self.device, dtype=torch.float32)   # [3, C, 3, 3, 3]
+        co, ci = w.shape[0], w.shape[1]
+        wh = torch.zeros((9, 4, 3, ci), dtype=torch.float32, device=self.device)                       # [tap, co, dt, ci]
+        wh[:, :co] = w.permute(3, 4, 0, 2, 1).reshape(9, co, 3, ci)
+        self.head_taps = wh.reshape(36, 3 * ci).to(torch.bfloat16).contiguous()
+        self.head_zero_bias = torch.zeros(40, dtype=torch.bfloat16, device=self.device)
+        self.head_bias = state_dict["decoder.head.2.bias"].detach().to(device=self.device, dtype=torch.bfloat16).float()
 
     @classmethod
     def from_reference(cls, vae, device="cuda"):
@@ -232,8 +241,8 @@ class WanVideoVAEB200:
             else:
                 x, xn = self._upsample(name, x, temporal, next_norm)
         del x
-        out, _ = self._conv3d(p + "head.2", xn, pad=(2, 1, 1), ncthw=True)
-        return out
+        part, _ = capi.conv3d_cl(xn, self.head_taps, self.head_zero_bias, kernel=(3, 1, 1), pad=(2, 0, 0))
+        return capi.vae_head_gather(part, self.head_bias, self.conv[p + "head.2"].cout)
 
     def _encode_clip(self, video: torch.Tensor) -> torch.Tensor:
         """video: (3, T, H, W) bf16 on the device, T = 1 + 4k -> mu (16, 1+k, H/8, W/8) normalised

@@ -194,6 +194,13 @@ int gf_vae_planes_to_cl_bf16(const void* src, long long N, int C, void* dst, lon
 int gf_vae_cl_to_planes_bf16(const void* src, long long ld, long long N, int C, void* dst, const float* mean,
                              const float* inv_std, int mode, void* stream);
 
+/* Decoder head (3x3x3 convolution to C <= 4 channels, :801-803) in two steps: gf_conv3d_cl_bf16 with a (3,1,1) kernel
+ * whose output channel tap*4 + co holds the partial sum of spatial tap (dh, dw) = (tap / 3, tap % 3), then this gather:
+ *   out[co, t, h, w] = bias[co] + sum_tap D[t, h + dh - 1, w + dw - 1, tap*4 + co]       (zero outside the frame)
+ * D: [T*H*W][ld] bf16 (ld >= 36), bias: fp32 [C] on the device, out: (C, T, H, W) bf16. */
+int gf_vae_head_gather_bf16(const void* D, long long ld, const float* bias, void* out, int C, int T, int H, int W,
+                            void* stream);
+
 /* Tile blending of WanVideoVAE.tiled_decode / tiled_encode (:1133-1153,1184-1204).
  * blend: values[c][t][h0+y][w0+x] += tile[c][t][y][x] * mask[y][x] (bf16 rounding after the product and after the sum).
  * blend_finish: values /= weight[h][w] (NULL: skip) and clamp to [-1, 1] when clamp != 0 (single_decode :1214-1217). */

@@ -146,6 +146,18 @@ def test_rowwise_kernels_against_torch(capi):
     back = capi.vae_cl_to_planes(cl, 16, mean=mean, inv_std=inv_std)
     wantb = _bf(_bf(cl.permute(3, 0, 1, 2) - _bf(mean).view(-1, 1, 1, 1)) * _bf(inv_std).view(-1, 1, 1, 1))
     assert torch.equal(back, wantb)
+    # head gather: nine taps x (3 + 1) partial-sum channels -> 3 planes
+    T, H, W = 2, 5, 7
+    Dp = _bf(torch.randn(T, H, W, 40, generator=g)).cuda()
+    hb = torch.randn(3, generator=g).cuda()
+    got = capi.vae_head_gather(Dp, hb, 3)
+    want = torch.zeros(3, T, H, W, device="cuda")
+    padded = F.pad(Dp.float().permute(3, 0, 1, 2), (1, 1, 1, 1))                 # (40, T, H+2, W+2)
+    for dh in range(3):
+        for dw in range(3):
+            want += padded[(dh * 3 + dw) * 4:(dh * 3 + dw) * 4 + 3, :, dh:dh + H, dw:dw + W]
+    want = _bf(want + hb.view(3, 1, 1, 1))
+    assert float((got.float() - want.float()).abs().max()) <= 0.07 and O.rel_l2(got.float(), want.float()) < 3e-3   # <= 1 bf16 ulp
     # blending: two torch bf16 ops
     values = _bf(torch.randn(3, 2, 10, 12, generator=g)).cuda()
     tile = _bf(torch.randn(3, 2, 4, 5, generator=g)).cuda()
