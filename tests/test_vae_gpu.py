@@ -100,6 +100,50 @@ def test_conv3d_against_torch(capi, case):
         assert O.rel_l2(sep.float(), yn.float()) < 1e-3
 
 
+def _sweep_cases():
+    """Seeded random 3x3-window shapes for the halo kernels (narrow: Cout <= 128, wide: one accumulator, n-tiles) and the
+    tap form (forced): odd frame sizes, single frames, frames narrower than a tile, Cin with a partial last k-block."""
+    import random
+    rng = random.Random(20260117)
+    cases = []
+    for i in range(24):
+        cin = rng.choice([8, 16, 32, 64, 96, 160, 192])
+        cout = rng.choice([3, 16, 32, 48, 96, 128, 136, 192, 256, 384])
+        T = rng.choice([1, 2, 3, 5])
+        H = rng.choice([1, 5, 16, 17, 33, 40])
+        W = rng.choice([3, 8, 9, 16, 23, 52])
+        kt = rng.choice([1, 3])
+        cases.append((f"sweep{i}_c{cin}to{cout}_{T}x{H}x{W}_kt{kt}", cin, cout, (T, H, W), kt, rng.choice([0, 0, 1, 2])))
+    return cases
+
+
+@pytest.mark.parametrize("case", _sweep_cases(), ids=[c[0] for c in _sweep_cases()])
+def test_conv3d_window_sweep(capi, case):
+    name, cin, cout, (T, H, W), kt, impl = case
+    g = torch.Generator(device="cpu").manual_seed(sum(name.encode()))
+    x = _bf(torch.randn(cin, T, H, W, generator=g)).cuda()
+    w = _bf(torch.randn(cout, cin, kt, 3, 3, generator=g) * (cin * kt * 9) ** -0.5).cuda()
+    b = _bf(torch.randn(cout, generator=g) * 0.1).cuda()
+    ref = _bf(F.conv3d(F.pad(x.float(), (1, 1, 1, 1, kt - 1, 0)).unsqueeze(0), w.float(), b.float())[0]).float()
+    use_res = cout % 8 == 0
+    res = _bf(torch.randn(cout, T, H, W, generator=g)).cuda() if use_res else None
+    if use_res:
+        ref = _bf(ref + res.float()).float()
+    bias = torch.zeros((cout + 7) // 8 * 8, dtype=torch.bfloat16, device="cuda")
+    bias[:cout] = b
+    capi.conv_tuning(impl)            # 0: per shape (pair kernels), 1: tap form, 2: halo on single CTAs
+    try:
+        y, _ = capi.conv3d_cl(_cl(x), _w2d(w, cin), bias, kernel=(kt, 3, 3), pad=(kt - 1, 1, 1),
+                              residual=_cl(res) if use_res else None, cout=cout)
+        torch.cuda.synchronize()
+    finally:
+        capi.conv_tuning(0)
+    got = y.float().permute(3, 0, 1, 2)
+    assert float(got[cout:].abs().max()) == 0.0 if got.shape[0] > cout else True      # padded channels are exact zeros
+    err = O.rel_l2(got[:cout], ref)
+    assert err < 3e-3, f"{name} impl {impl}: rel_l2 {err:.3e}, max abs {float((got[:cout] - ref).abs().max()):.3e}"
+
+
 def test_rowwise_kernels_against_torch(capi):
     g = torch.Generator(device="cpu").manual_seed(3)
     for C in (32, 96, 192, 384):
