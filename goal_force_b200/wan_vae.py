@@ -294,14 +294,19 @@ class WanVideoVAEB200:
         return x
 
     def build_mask(self, data, is_bound, border_width):
+        """WanVideoVAE.build_mask (:1094-1106): fp32 (1, 1, 1, H, W) blending ramp for a tile of `data`'s H x W."""
         H, W = data.shape[-2], data.shape[-1]
-        key = (H, W, tuple(is_bound), tuple(border_width))
+        h = self.build_1d_mask(H, is_bound[0], is_bound[1], border_width[0]).view(H, 1).expand(H, W)
+        w = self.build_1d_mask(W, is_bound[2], is_bound[3], border_width[1]).view(1, W).expand(H, W)
+        return torch.stack([h, w]).min(dim=0).values.view(1, 1, 1, H, W)
+
+    def _mask_dev(self, tile, is_bound, border_width):
+        """build_mask(...).to(bf16) on the device as an [H, W] plane (what the reference multiplies with), cached."""
+        key = (tile.shape[-2], tile.shape[-1], tuple(is_bound), tuple(border_width))
         m = self._masks.get(key)
         if m is None:
-            h = self.build_1d_mask(H, is_bound[0], is_bound[1], border_width[0]).view(H, 1).expand(H, W)
-            w = self.build_1d_mask(W, is_bound[2], is_bound[3], border_width[1]).view(1, W).expand(H, W)
-            m = torch.stack([h, w]).min(dim=0).values.to(device=self.device, dtype=torch.bfloat16).contiguous()
-            self._masks[key] = m
+            m = self.build_mask(tile, is_bound, border_width)[0, 0, 0].to(device=self.device, dtype=torch.bfloat16)
+            m = self._masks[key] = m.contiguous()
         return m
 
     @staticmethod
@@ -359,7 +364,7 @@ class WanVideoVAEB200:
             return self._decode_clip(z[:, :, h:h_, w:w_].contiguous())
 
         for (h, h_, w, w_), tile in self._tiles(tasks, decode_tile, shape_of, group):
-            mask = self.build_mask(tile, (h == 0, h_ >= H, w == 0, w_ >= W), border)
+            mask = self._mask_dev(tile, (h == 0, h_ >= H, w == 0, w_ >= W), border)
             capi.vae_blend_(values, tile, mask, h * up, w * up)
             one = ones.setdefault(tuple(mask.shape), torch.ones((1, 1) + tuple(mask.shape), dtype=torch.bfloat16,
                                                                 device=self.device))
@@ -388,7 +393,7 @@ class WanVideoVAEB200:
             return self._encode_clip(v[:, :, h:h_, w:w_].contiguous())
 
         for (h, h_, w, w_), tile in self._tiles(tasks, encode_tile, shape_of, group):
-            mask = self.build_mask(tile, (h == 0, h_ >= H, w == 0, w_ >= W), border)
+            mask = self._mask_dev(tile, (h == 0, h_ >= H, w == 0, w_ >= W), border)
             capi.vae_blend_(values, tile, mask, h // up, w // up)
             one = ones.setdefault(tuple(mask.shape), torch.ones((1, 1) + tuple(mask.shape), dtype=torch.bfloat16,
                                                                 device=self.device))

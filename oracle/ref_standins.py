@@ -124,3 +124,38 @@ def controlnet_standin_from_cfg(cfg, num_layers, state_dict=None, stride=None, d
     if state_dict is not None:
         m.load_state_dict(state_dict, strict=True)
     return m.to(device=device, dtype=dtype).eval()
+
+
+class _ParamTree(nn.Module):
+    """A module tree built from dotted parameter names (numeric components become attribute names of sub-modules, as
+    nn.Sequential / nn.ModuleList register them), so that state_dict() returns exactly the given keys."""
+
+    def __init__(self, state_dict: dict):
+        super().__init__()
+        for name, value in state_dict.items():
+            mod = self
+            parts = name.split(".")
+            for part in parts[:-1]:
+                if part not in mod._modules:
+                    mod.add_module(part, _ParamTree({}))
+                mod = mod._modules[part]
+            mod.register_parameter(parts[-1], nn.Parameter(value.clone(), requires_grad=False))
+
+
+class VideoVAEStandIn(_ParamTree):
+    """VideoVAE_ (diffsynth/models/wan_video_vae.py:842-1055) as goal_force_b200.wan_vae reads it: `.z_dim`,
+    `.encoder.conv1.weight` (width) and `state_dict()` with the reference's key names."""
+
+    def __init__(self, state_dict: dict, z_dim: int = 16):
+        super().__init__(state_dict)
+        self.z_dim = z_dim
+
+
+class WanVideoVAEStandIn(nn.Module):
+    """WanVideoVAE (:1057-1080): `.model` (VideoVAE_), `.upsampling_factor`, `.z_dim`."""
+
+    def __init__(self, state_dict: dict, z_dim: int = 16):
+        super().__init__()
+        self.model = VideoVAEStandIn(state_dict, z_dim)
+        self.upsampling_factor = 8
+        self.z_dim = z_dim

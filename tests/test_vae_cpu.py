@@ -63,3 +63,28 @@ def test_state_dict_keys_match_live_reference():
     assert sorted(ref) == sorted(sd)
     for k in ref:
         assert ref[k].shape == sd[k].shape, k
+
+
+def test_standin_module_exposes_the_reference_surface(golden_dir):
+    """The nn.Module stand-in used by the GPU drop-in test has the attribute surface `WanVideoVAEB200.from_reference`
+    reads (model.z_dim, model.encoder.conv1.weight, model.state_dict() with the reference's keys)."""
+    from oracle.ref_standins import WanVideoVAEStandIn
+    g, sd = _case(golden_dir)
+    m = WanVideoVAEStandIn(sd)
+    assert sorted(m.model.state_dict()) == sorted(sd)
+    assert m.model.encoder.conv1.weight.shape[0] == g["dim"] and m.model.z_dim == 16 and m.upsampling_factor == 8
+    for k, v in m.model.state_dict().items():
+        assert torch.equal(v, sd[k])
+
+
+@pytest.mark.reference
+def test_standin_matches_live_reference_attributes():
+    from oracle import ref_shim
+    from oracle.ref_standins import WanVideoVAEStandIn
+    vae = ref_shim.load_module("diffsynth.models.wan_video_vae")
+    ref = vae.WanVideoVAE(z_dim=16)
+    ref.model = vae.VideoVAE_(dim=32, z_dim=16)
+    m = WanVideoVAEStandIn(V.random_state_dict(dim=32))
+    assert sorted(m.model.state_dict()) == sorted(ref.model.state_dict())
+    assert m.model.z_dim == ref.model.z_dim and m.upsampling_factor == ref.upsampling_factor
+    assert m.model.encoder.conv1.weight.shape == ref.model.encoder.conv1.weight.shape

@@ -295,3 +295,24 @@ def test_real_width_clip_against_oracle():
         budget = _bf16_oracle_err(V.encode, sd, video, wante)
         print(f"vae encode (dim 96): ours {erre:.3e}  oracle-bf16 {budget:.3e}")
         assert erre <= max(budget, 4e-3), (erre, budget)
+
+
+def test_from_reference_module_is_a_drop_in(golden_dir):
+    """INTEGRATION.md recipe: `pipe.vae = WanVideoVAEB200.from_reference(pipe.vae)` with an nn.Module that carries the
+    reference's attribute tree, then the reference's call signatures (`encode(videos, device=, tiled=, tile_size=,
+    tile_stride=)`, `decode(...)`) with the pipeline's argument meaning."""
+    from goal_force_b200.wan_vae import WanVideoVAEB200
+    from oracle.ref_standins import WanVideoVAEStandIn
+    g, sd = _golden(golden_dir)
+    ref_module = WanVideoVAEStandIn(sd).cuda()
+    vae = WanVideoVAEB200.from_reference(ref_module, device="cuda")
+    assert vae.dim == g["dim"] and vae.z_dim == 16 and vae.upsampling_factor == 8
+    video = vae.decode(g["z_big"].to(torch.bfloat16), device="cuda", tiled=True, tile_size=(4, 5), tile_stride=(3, 3))
+    assert video.shape == g["tiled_decode"].shape and video.is_cuda and video.dtype == torch.bfloat16
+    assert O.rel_l2(video.float().cpu(), g["tiled_decode"].float()) < 2e-2
+    lat = vae.encode([video[0]], device="cuda", tiled=True, tile_size=(4, 5), tile_stride=(3, 3))
+    assert lat.shape == g["tiled_encode"].shape
+    assert O.rel_l2(lat.float().cpu(), g["tiled_encode"]) < 2e-2
+    # build_mask: the reference's formula (data tensor in, (1,1,1,H,W)-broadcastable mask out)
+    m = vae.build_mask(torch.empty(1, 3, 5, 16, 24), (True, False, False, True), (8, 8))
+    assert m.shape == (1, 1, 1, 16, 24) and torch.equal(m, V.build_mask(16, 24, (True, False, False, True), (8, 8)))
