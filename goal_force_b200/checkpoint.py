@@ -64,3 +64,33 @@ def load_controlnet(path, cfg, num_layers: int, stride=None, device="cuda"):
     """ControlNetB200 from a goal-force training checkpoint (step-N.safetensors; keys carry 'pipe.controlnet.')."""
     from .wan_dit import ControlNetB200
     return ControlNetB200(cfg, SafetensorsStateDict(path), num_layers, stride=stride, device=device)
+
+
+def read_vae_state_dict(path) -> dict:
+    """VideoVAE_ state dict from a Wan2.1 VAE checkpoint, in the key names WanVideoVAEB200 consumes.  Accepts what the
+    reference's loader accepts (diffsynth/models/wan_video_vae.py:1256-1267): a torch pickle (Wan2.1_VAE.pth), optionally
+    wrapped in {'model_state': ...}, or a .safetensors file; keys with the wrapper's 'model.' prefix (what
+    WanVideoVAEStateDictConverter.from_civitai produces for WanVideoVAE) are accepted as well.  254 MB: read eagerly."""
+    path = Path(path)
+    if not path.exists():
+        raise FileNotFoundError(path)
+    if path.suffix == ".safetensors":
+        from safetensors.torch import load_file
+        sd = load_file(str(path), device="cpu")
+    else:
+        sd = torch.load(str(path), map_location="cpu", weights_only=True)
+    if "model_state" in sd:
+        sd = sd["model_state"]
+    if sd and all(k.startswith("model.") for k in sd):
+        sd = {k[len("model."):]: v for k, v in sd.items()}
+    for need in ("encoder.conv1.weight", "decoder.conv1.weight", "conv1.weight", "conv2.weight", "decoder.head.2.weight"):
+        if need not in sd:
+            raise KeyError(f"{path}: not a Wan2.1 VideoVAE_ checkpoint (missing {need})")
+    return sd
+
+
+def load_vae(path, device="cuda"):
+    """WanVideoVAEB200 from a Wan2.1 VAE checkpoint file (width and z_dim are read off the weights)."""
+    from .wan_vae import WanVideoVAEB200
+    sd = read_vae_state_dict(path)
+    return WanVideoVAEB200(sd, dim=sd["encoder.conv1.weight"].shape[0], z_dim=sd["conv2.weight"].shape[0], device=device)

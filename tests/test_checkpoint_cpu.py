@@ -31,3 +31,26 @@ def test_controlnet_checkpoint_prefix(tmp_path):
     assert torch.equal(sd["controlnet_zero_convs_after.0.bias"], w)       # as load_controlnet_weights strips it
     with pytest.raises(KeyError):
         sd["controlnet_zero_convs_after.1.bias"]
+
+
+def test_vae_checkpoint_forms(tmp_path):
+    """read_vae_state_dict accepts the forms the reference's loader accepts: plain pickle, {'model_state': ...},
+    'model.'-prefixed keys, safetensors; anything else is refused."""
+    import pytest
+    from safetensors.torch import save_file
+    from goal_force_b200.checkpoint import read_vae_state_dict
+    from oracle import wan_vae_oracle as V
+    sd = V.random_state_dict(dim=32, seed=0)
+    torch.save(sd, tmp_path / "plain.pth")
+    torch.save({"model_state": sd}, tmp_path / "wrapped.pth")
+    torch.save({"model." + k: v for k, v in sd.items()}, tmp_path / "prefixed.pth")
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(tmp_path / "vae.safetensors"))
+    for name in ("plain.pth", "wrapped.pth", "prefixed.pth", "vae.safetensors"):
+        got = read_vae_state_dict(tmp_path / name)
+        assert sorted(got) == sorted(sd), name
+        assert torch.equal(got["decoder.head.2.weight"], sd["decoder.head.2.weight"])
+    torch.save({"foo": torch.zeros(1)}, tmp_path / "other.pth")
+    with pytest.raises(KeyError):
+        read_vae_state_dict(tmp_path / "other.pth")
+    with pytest.raises(FileNotFoundError):
+        read_vae_state_dict(tmp_path / "missing.pth")
