@@ -316,3 +316,34 @@ def test_from_reference_module_is_a_drop_in(golden_dir):
     # build_mask: the reference's formula (data tensor in, (1,1,1,H,W)-broadcastable mask out)
     m = vae.build_mask(torch.empty(1, 3, 5, 16, 24), (True, False, False, True), (8, 8))
     assert m.shape == (1, 1, 1, 16, 24) and torch.equal(m, V.build_mask(16, 24, (True, False, False, True), (8, 8)))
+
+
+def test_job_driver_callables_on_the_b200_vae(golden_dir):
+    """jobs.vae_control_encoder / jobs.vae_image_condition: the two VAE call sites that feed the denoiser
+    (src/goal_force/wan_video_new.py:798-805 and :894-916) on WanVideoVAEB200, against the oracle."""
+    from goal_force_b200 import jobs
+    from goal_force_b200.pipeline import first_frame_mask
+    from goal_force_b200.wan_vae import WanVideoVAEB200
+    g, sd = _golden(golden_dir)
+    dim = g["dim"]
+    vae = WanVideoVAEB200(sd, dim=dim)
+    gen = torch.Generator().manual_seed(9)
+    control = torch.rand(9, 32, 48, 3, generator=gen).to(torch.bfloat16)            # (F, H, W, 3) as the dataset yields it
+    lat = jobs.vae_control_encoder(vae, tiled=False)(control)
+    with torch.no_grad():
+        want = V.encode(sd, control.float().permute(3, 0, 1, 2).unsqueeze(0), dim=dim)
+    assert lat.shape == (1, 16, 3, 4, 6) and lat.dtype == torch.bfloat16 and lat.is_cuda
+    assert O.rel_l2(lat.float().cpu(), want) < 2e-2
+    tiled = jobs.vae_control_encoder(vae, tiled=True, tile_size=(3, 4), tile_stride=(2, 2))(control)
+    with torch.no_grad():
+        want_t = V.tiled_encode(sd, control.float().permute(3, 0, 1, 2).unsqueeze(0), (24, 32), (16, 16), dim=dim)
+    assert O.rel_l2(tiled.float().cpu(), want_t) < 2e-2
+    image = (torch.rand(3, 32, 48, generator=gen) * 2 - 1).to(torch.bfloat16)
+    y = jobs.vae_image_condition(vae, image, num_frames=9, tiled=False)
+    assert y.shape == (1, 20, 3, 4, 6)
+    assert torch.equal(y[0, :4].float().cpu(), first_frame_mask(9, 4, 6).float())
+    clip = torch.zeros(1, 3, 9, 32, 48)
+    clip[0, :, 0] = image.float()
+    with torch.no_grad():
+        want_y = V.encode(sd, clip, dim=dim)
+    assert O.rel_l2(y[0, 4:].float().cpu(), want_y[0]) < 2e-2

@@ -16,4 +16,5 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gf_ -c 40 -f -o $OUT/${TAG}_block \
     python bench.py --steps 1 --warmup 0 --layers 1 --controlnet-layers 0 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
+timeout 600 python tools/bench_vae.py --out $OUT/${TAG}_vae_bench.json > $OUT/${TAG}_vae_bench.log 2>&1
 tail -5 $OUT/${TAG}_pytest_gpu.log; cat $OUT/${TAG}_smoke.log | tail -3; cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
