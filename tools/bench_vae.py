@@ -110,6 +110,26 @@ def main():
             zt = z[:, :, :, :30, :52].contiguous()
             section("eager_bf16_decode_one_tile_30x52", lambda: V.decode(sdb, zt))
             ours_tile = section("ours_decode_one_tile_30x52", lambda: vae._decode_clip(zt[0]))
+            # parity at full tile size (81 x 240 x 416) against the fp32 oracle on this GPU: ours and the oracle's bf16 run
+            try:
+                torch.backends.cudnn.allow_tf32 = False
+                torch.backends.cuda.matmul.allow_tf32 = False
+                sdf = {k: v.to(device="cuda", dtype=torch.float32) for k, v in sd.items()}
+                want = V.decode(sdf, zt.float())[0]
+                res["tile_decode_rel_l2_vs_fp32_oracle"] = {
+                    "ours": O.rel_l2(ours_tile.float(), want),
+                    "oracle_bf16": O.rel_l2(V.decode(sdb, zt)[0].float(), want)}
+                vt = video[:, :, :, :240, :416].contiguous()
+                want_e = V.encode(sdf, vt.float())[0]
+                res["tile_encode_rel_l2_vs_fp32_oracle"] = {
+                    "ours": O.rel_l2(vae._encode_clip(vt[0]).float(), want_e),
+                    "oracle_bf16": O.rel_l2(V.encode(sdb, vt)[0].float(), want_e)}
+                print({k: v for k, v in res.items() if "fp32_oracle" in k}, flush=True)
+                del sdf, want, want_e
+            except Exception as e:  # noqa: BLE001
+                res["tile_parity_error"] = repr(e)[:300]
+            torch.cuda.empty_cache()
+            dump()
             eager_full = section("eager_bf16_single_decode", lambda: V.decode(sdb, z))
             if eager_full is not None and single_dec is not None:
                 # parity at full size: ours vs the eager bf16 run, relative to the eager run's own scale
