@@ -33,6 +33,7 @@ SIGNATURES = {
     "gf_ctx_destroy": [_p],
     "gf_ctx_set_attention": [_p, _i, _i],
     "gf_ctx_set_gemm_raster": [_p, _i],
+    "gf_ctx_set_gemm_tile": [_p, _i],
     "gf_ctx_set_conv": [_p, _i],
     "gf_ctx_stats": [_p, ctypes.POINTER(_ll), ctypes.POINTER(_ll), ctypes.POINTER(_ll)],
     "gf_gemm_bf16": [_p, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p, _i, _p, _p, _ll, _i, _p],
@@ -127,6 +128,9 @@ def ctx() -> int:
         emu = int(os.environ.get("GF_ATTN_EMU_PAIRS", "-1"))
         if impl or emu >= 0:
             _check(load().gf_ctx_set_attention(c, impl, emu), "gf_ctx_set_attention")
+        gb = int(os.environ.get("GF_GEMM_BN", "0"))
+        if gb:
+            _check(load().gf_ctx_set_gemm_tile(c, gb), "gf_ctx_set_gemm_tile")
         ci = int(os.environ.get("GF_CONV_IMPL", "0"))
         if ci:
             _check(load().gf_ctx_set_conv(c, ci), "gf_ctx_set_conv")
@@ -317,6 +321,11 @@ def attention_tuning(impl: int = 0, emu_pairs: int = -1) -> None:
     """Select the attention kernel of this process's context (0 = per shape, 80 = decoupled 80-row blocks,
     128 = aliased 128-row blocks) and the share of exponentials evaluated on the FMA pipe (-1 = kernel default)."""
     _check(load().gf_ctx_set_attention(ctx(), impl, emu_pairs), "gf_ctx_set_attention")
+
+
+def gemm_tile_tuning(bn: int = 0) -> None:
+    """Tile width of the CTA-pair GEMM for this process's context: 0 = per shape, 224 / 256 = forced."""
+    _check(load().gf_ctx_set_gemm_tile(ctx(), bn), "gf_ctx_set_gemm_tile")
 
 
 def conv_tuning(impl: int = 0) -> None:

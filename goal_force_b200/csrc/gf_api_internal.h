@@ -35,6 +35,7 @@ struct CtxTuning {
                            // (160 = CTA-pair variant of 80)
   int attn_emu = -1;       // -1: kernel default; 0, 2, 4, 6: column pairs per 16 with exp2 on the FMA pipe
   int gemm_group_m = 0;    // 0: per shape; > 0: rasterisation group height in m-tiles
+  int gemm_bn = 0;         // pair GEMM tile width: 0 = per shape (cost model), 224 or 256 = forced
   int conv_impl = 0;       // 0: per shape (halo form, as a CTA pair, for 3x3 windows with Cout <= 128); 1: always
                            // tap-by-tap; 2: halo form on single CTAs
 };

@@ -32,10 +32,12 @@ constexpr int GEMM_UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_GROUP_M = 8;    // default rasterisation: tiles walk 8 m-tiles before moving along N (L2 reuse of W)
 
-template <int kCG> struct GemmCfg {
-  static constexpr int kBRows = GEMM_BN / kCG;                           // W rows staged by each CTA
+// kBN = columns per tile: 256, or 224 for shapes whose 256-wide tiling leaves the last wave of the 74 SM pairs mostly
+// empty (M = 4095 rows per GPU at 8 GPUs with N = 5120: 320 tiles = 4.3 waves; 224-wide: 368 tiles = 4.97 waves).
+template <int kCG, int kBN = GEMM_BN> struct GemmCfg {
+  static constexpr int kBRows = kBN / kCG;                               // W rows staged by each CTA
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;                  // 16 KB
-  static constexpr int kBBytes = kBRows * GEMM_BK * 2;                   // 32 KB / 16 KB
+  static constexpr int kBBytes = kBRows * GEMM_BK * 2;                   // 32 KB / 16 KB (14 KB at kBN = 224)
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kCG == 1) ? 4 : 6;                     // 192 KB of operand ring either way
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -75,10 +77,10 @@ template <int EPI> __device__ __forceinline__ float epi_act(float v) {
   }
 }
 
-template <int kCG, int EPI>
+template <int kCG, int EPI, int kBN = GEMM_BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<kCG>;
+  using Cfg = GemmCfg<kCG, kBN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
@@ -132,7 +134,7 @@ gf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         int mt, nt; tile_coords(t, p.num_m_tiles, p.num_n_tiles, p.group_m, mt, nt);
         const int m0 = (mt * kCG + (int)cta_rank) * GEMM_BM;
-        const int n0 = nt * GEMM_BN + (int)cta_rank * Cfg::kBRows;
+        const int n0 = nt * kBN + (int)cta_rank * Cfg::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if constexpr (kCG == 1) {
@@ -153,7 +155,7 @@ gf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = idesc_bf16(GEMM_BM * kCG, GEMM_BN, 0, 0);
+      constexpr uint32_t idesc = idesc_bf16(GEMM_BM * kCG, kBN, 0, 0);
       constexpr uint64_t dbase = smem_desc_base(/*sbo=*/1024, /*lbo=*/16);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -185,7 +187,7 @@ gf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       int mt, nt; tile_coords(t, p.num_m_tiles, p.num_n_tiles, p.group_m, mt, nt);
       const int row = (mt * kCG + (int)cta_rank) * GEMM_BM + q * 32 + (int)lane;
-      const int n0 = nt * GEMM_BN;
+      const int n0 = nt * kBN;
       const bool row_ok = row < p.M;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -193,7 +195,7 @@ gf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __nv_bfloat16* crow = (EPI == GF_EPI_F32) ? p.C : p.C + (long long)row * p.ldc + n0;
       const __nv_bfloat16* rrow = (EPI == GF_EPI_GATE_RES) ? p.R + (long long)row * p.ldr + n0 : nullptr;
 #pragma unroll 1
-      for (int c = 0; c < GEMM_BN / 32; ++c) {
+      for (int c = 0; c < kBN / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(t_addr + c * 32, v);
         tmem_ld_wait();
@@ -274,10 +276,10 @@ gf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------ host side
-template <int kCG, int EPI>
+template <int kCG, int EPI, int kBN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<kCG>;
-  auto kern = gf_gemm_kernel<kCG, EPI>;
+  using Cfg = GemmCfg<kCG, kBN>;
+  auto kern = gf_gemm_kernel<kCG, EPI, kBN>;
   static bool configured[64] = {};
   if (int rc = gf_set_smem_once(configured, reinterpret_cast<const void*>(kern), Cfg::kSmemBytes)) return rc;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
@@ -298,16 +300,32 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return (int)cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
 }
 
-template <int kCG>
+template <int kCG, int kBN>
 static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t s) {
   switch (epi) {
-    case GF_EPI_BIAS: return launch_gemm<kCG, GF_EPI_BIAS>(a, b, p, s);
-    case GF_EPI_BIAS_GELU: return launch_gemm<kCG, GF_EPI_BIAS_GELU>(a, b, p, s);
-    case GF_EPI_BIAS_SILU: return launch_gemm<kCG, GF_EPI_BIAS_SILU>(a, b, p, s);
-    case GF_EPI_GATE_RES: return launch_gemm<kCG, GF_EPI_GATE_RES>(a, b, p, s);
-    case GF_EPI_F32: return launch_gemm<kCG, GF_EPI_F32>(a, b, p, s);
+    case GF_EPI_BIAS: return launch_gemm<kCG, GF_EPI_BIAS, kBN>(a, b, p, s);
+    case GF_EPI_BIAS_GELU: return launch_gemm<kCG, GF_EPI_BIAS_GELU, kBN>(a, b, p, s);
+    case GF_EPI_BIAS_SILU: return launch_gemm<kCG, GF_EPI_BIAS_SILU, kBN>(a, b, p, s);
+    case GF_EPI_GATE_RES: return launch_gemm<kCG, GF_EPI_GATE_RES, kBN>(a, b, p, s);
+    case GF_EPI_F32: return launch_gemm<kCG, GF_EPI_F32, kBN>(a, b, p, s);
     default: return GF_ERR_BAD_ARG;
   }
+}
+
+// Tile width for the pair GEMM.  Tiles run in waves of one per SM pair; a mostly empty last wave costs more than its
+// share (measured under the sustained power cap, tools/gemm_tile_bench.py, 256- vs 224-wide, alternating samples):
+//   M = 4095 (8-way sequence parallel), N = 5120: 320 tiles = 4.3 waves vs 368 = 4.97: 224 is 22 % (K = 5120) and 26 %
+//   (K = 13824) faster; M = 8190, N = 5120: 8.65 vs 9.95 waves: +4 %; N = 13824 / 15360 at M = 4095: 11.7 / 12.97 waves,
+//   equal; M = 32760: 224 is 5 % slower (its smaller tile moves 134 B/clk through shared memory per MMA cycle, the
+//   256-wide one exactly the 128 B/clk the SM has).  So: 224 only for short launches whose wave efficiency it lifts.
+static int choose_bn(int M, int N, int pairs) {
+  if (pairs <= 0) return GEMM_BN;
+  const long long m_tiles = (M + 255) / 256;
+  const long long t256 = m_tiles * ((N + 255) / 256), t224 = m_tiles * ((N + 223) / 224);
+  const long long w256 = (t256 + pairs - 1) / pairs, w224 = (t224 + pairs - 1) / pairs;
+  const double e256 = (double)M * N / ((double)w256 * pairs * 256.0 * 256.0);
+  const double e224 = (double)M * N / ((double)w224 * pairs * 256.0 * 224.0);
+  return (N > 256 && t256 >= pairs && w256 <= 12 && e224 > e256 + 0.02) ? 224 : GEMM_BN;
 }
 
 }  // namespace gf
@@ -326,8 +344,10 @@ extern "C" int gf_gemm_bf16(gf_ctx* ctx, const void* A, long long lda, const voi
   int rc = 0;
   const CUtensorMap* tmA = gf_ctx_tmap(ctx, &scrA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM, &rc);
   if (!tmA) return rc;
+  const int forced_bn = gf_ctx_tuning(ctx).gemm_bn;
+  const int bn = cta_group == 2 ? (forced_bn > 0 ? forced_bn : choose_bn(M, N, gf_num_sms() / 2)) : GEMM_BN;
   const CUtensorMap* tmB =
-      gf_ctx_tmap(ctx, &scrB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GEMM_BK, GEMM_BN / cta_group, &rc);
+      gf_ctx_tmap(ctx, &scrB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GEMM_BK, bn / cta_group, &rc);
   if (!tmB) return rc;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
@@ -336,12 +356,13 @@ extern "C" int gf_gemm_bf16(gf_ctx* ctx, const void* A, long long lda, const voi
   p.gate = reinterpret_cast<const __nv_bfloat16*>(gate);
   p.R = reinterpret_cast<const __nv_bfloat16*>(R); p.ldr = ldr;
   p.num_m_tiles = (M + GEMM_BM * cta_group - 1) / (GEMM_BM * cta_group);
-  p.num_n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
+  p.num_n_tiles = (N + bn - 1) / bn;
   // Rasterisation: tiles walk `group_m` m-tiles before moving along N.  Measured under sustained load at M = 32760
   // (tools/gpu_check.py gemm_sustained): 16 is best for K = 5120 (each operand slab of a tile is 2.6 MB), 8 for
   // K = 13824 (7 MB slabs: a taller group no longer fits L2 next to the W columns in flight); 4 and 32 lose 6-10 %.
   const int forced = gf_ctx_tuning(ctx).gemm_group_m;
   p.group_m = forced > 0 ? forced : (K <= 8192 ? 2 * GEMM_GROUP_M : GEMM_GROUP_M);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  return cta_group == 1 ? dispatch_epi<1>(epi, *tmA, *tmB, p, s) : dispatch_epi<2>(epi, *tmA, *tmB, p, s);
+  if (cta_group == 1) return dispatch_epi<1, GEMM_BN>(epi, *tmA, *tmB, p, s);
+  return bn == 224 ? dispatch_epi<2, 224>(epi, *tmA, *tmB, p, s) : dispatch_epi<2, GEMM_BN>(epi, *tmA, *tmB, p, s);
 }

@@ -156,6 +156,12 @@ extern "C" int gf_ctx_set_gemm_raster(gf_ctx* ctx, int group_m) {
   return 0;
 }
 
+extern "C" int gf_ctx_set_gemm_tile(gf_ctx* ctx, int bn) {
+  if (!ctx || (bn != 0 && bn != 224 && bn != 256)) return GF_ERR_BAD_ARG;
+  ctx->tuning.gemm_bn = bn;
+  return 0;
+}
+
 extern "C" int gf_ctx_set_conv(gf_ctx* ctx, int impl) {
   if (!ctx || impl < 0 || impl > 2) return GF_ERR_BAD_ARG;
   ctx->tuning.conv_impl = impl;

@@ -46,7 +46,8 @@ int gf_abi_version(void);
  * sequences the 80-row decoupled kernel, as a CTA pair when the 512-row work items fill the SM pairs; the 128-row
  * kernel for Lk <= 1024), 80 / 160 / 128 = forced (160 = CTA-pair form of 80); emu_pairs -1 = kernel default, or
  * 0/2/4/6 column pairs per 16 whose exp2 runs on the FMA pipe.  gf_ctx_set_gemm_raster: rasterisation group height in
- * m-tiles, 0 = per-shape choice.  gf_ctx_set_conv: impl 0 = per-shape choice of the convolution kernel (halo form for
+ * m-tiles, 0 = per-shape choice.  gf_ctx_set_gemm_tile: tile width of the CTA-pair GEMM, 0 = per-shape choice (256, or
+ * 224 where the 256-wide tiling would strand most of the last wave of SM pairs), 224 / 256 = forced.  gf_ctx_set_conv: impl 0 = per-shape choice of the convolution kernel (halo form for
  * 3x3 windows with Cout <= 128, as a CTA pair), 1 = always the tap-by-tap form, 2 = halo form on single CTAs.
  * gf_ctx_stats: descriptor-cache counters (any pointer may be NULL). */
 typedef struct gf_ctx gf_ctx;
@@ -54,6 +55,7 @@ int gf_ctx_create(gf_ctx** ctx);
 int gf_ctx_destroy(gf_ctx* ctx);
 int gf_ctx_set_attention(gf_ctx* ctx, int impl, int emu_pairs);
 int gf_ctx_set_gemm_raster(gf_ctx* ctx, int group_m);
+int gf_ctx_set_gemm_tile(gf_ctx* ctx, int bn);
 int gf_ctx_set_conv(gf_ctx* ctx, int impl);
 int gf_ctx_stats(gf_ctx* ctx, long long* tmap_entries, long long* tmap_hits, long long* tmap_misses);
 
