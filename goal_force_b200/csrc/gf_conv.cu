@@ -5,21 +5,24 @@
 // Replaces CausalConv3d (diffsynth/models/wan_video_vae.py:33-52), the Conv2d of Resample (:92-119) and the strided
 // time_conv (:104-119) of the reference.  The clip is channels-last ([T][H][W][C] bf16), so the GEMM is
 //   M = To*Ho*Wo output positions,  N = Cout,  K = taps * Cin,
-// and nothing is ever gathered into an im2col buffer: for every tap the TMA producer loads the SAME 4-D tensor map at
-// a shifted coordinate.  Rows of an M tile are a BH x BW patch of one output frame (BH*BW = 128); box elements outside
-// the clip (negative t: the causal front padding; h, w outside: the spatial zero padding) are zero-filled by TMA.
-// A strided convolution reads through one tensor map per input parity (base pointer offset, doubled pitches), so the
-// box stays dense in the map's own coordinates.
+// and nothing is ever gathered into an im2col buffer: the TMA producer loads boxes of ONE 4-D tensor map (C, W, H, T) at
+// shifted coordinates, and box elements outside the clip (negative t: the causal front padding; h, w outside: the
+// spatial zero padding) are zero-filled by TMA.
 //
-// Structure = gf_gemm.cu's single-CTA form: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue,
-// two 256-column accumulator stages.  A k-block is 64 channels of one tap; for Cin % 64 != 0 the last block of a tap
-// issues only the valid 16-wide MMAs (the TMA box is zero-filled, the weights beside it are never multiplied).
+// Two kernels (DESIGN 10 has the shared-memory-bandwidth model that decides between them):
+//   gf_conv3d_halo_kernel  3x3 spatial windows, stride 1 (95 % of the VAE's FLOPs): one input halo per (dt, channel
+//                          block) serves all nine taps through row-shifted UMMA descriptors; CTA pairs (cta_group::2).
+//   gf_conv3d_kernel       everything else (strided, 1x1, (3,1,1), folded windows): one 128-row box per tap, a tensor
+//                          map per input parity for stride 2; gf_gemm.cu's single-CTA skeleton (warp 0 TMA producer,
+//                          warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue, two 256-column accumulator stages).
+// A k-block is 64 channels of one tap; for Cin % 64 != 0 the last block of a tap issues only the valid 16-wide MMAs
+// (the TMA box is zero-filled, the weights beside it are never multiplied).
 //
-// Epilogue (per output position, fp32 accumulator):
+// Epilogue, shared by both (conv_epilogue_rows; per output position, fp32 accumulator):
 //   v  = bf16(acc + bias)                      ; v = bf16(v + R) when a residual is given (ResidualBlock tail, :296-301)
-//   Y  = v                                     (channels-last, or (C, T, H, W) for the 3-channel head)
+//   Y  = v                                     (channels-last, or (C, T, H, W) planes for Cout <= 32)
 //   Y2 = silu(v / max(|v|_2, 1e-12) * sqrt(C) * gamma)   (the NEXT layer's RMS_norm + SiLU, :55-70,283-288) when the
-//        whole channel row lives in one tile (Cout <= 256); two passes over the accumulator in TMEM.
+//        whole channel row lives in one tile (Cout <= 256); the row stays in registers between the two passes.
 #include <type_traits>
 #include "gf_ptx.cuh"
 #include "gf_api_internal.h"
@@ -380,21 +383,26 @@ gf_conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Halo form for 3x3 spatial windows with few output channels (Cout <= 128, stride 1).
+// Halo form for 3x3 spatial windows (stride 1).
 //
-// With N <= 128 the tap-by-tap form above is bound by operand traffic into the SM (about 56 B/clk/SM: 16 KB of A plus
-// N x 128 B of weights for 4 x 56 MMA cycles), not by the tensor core.  Here a CTA owns 32 x 8 output positions (two
-// 128-row accumulators) and, per (dt, 64-channel block), loads ONE 34 x 10 halo of the input (43.5 KB) instead of nine
-// shifted 128-row tiles: position (h, w) of the halo sits at row h*10 + w of a 128-byte-row, 128B-swizzled buffer, so
-// the A operand of tap (dh, dw) for accumulator `mh` is the same buffer read through a descriptor that starts at row
-// (mh*16 + dh)*10 + dw with a stride of 10 rows (1280 B) between 8-row groups -- the swizzle is a function of the
-// absolute shared-memory address for TMA and the tensor core alike (checked on B200: descriptors with the 'matrix base
-// offset' field set to (addr >> 7) & 7 give wrong results, plain start addresses are exact).  Each weight tile feeds both accumulators.
-// Operand bytes per MMA drop 3.3x (N = 96) and the kernel becomes tensor-bound.
+// The tap-by-tap form above moves 16 KB of A plus N x 128 B of weights into shared memory per k-block and reads them
+// back for 4 MMAs: with 128 B/clk of shared-memory bandwidth shared by the operand reads and the TMA fill it is bound
+// at 29 % (N = 96) to 60 % (N = 192) of the tensor rate.  Here a CTA owns a 16*MH x 8 patch of output positions and,
+// per (dt, 64-channel block), loads ONE (16*MH + 2) x 10 halo of the input instead of nine shifted 128-row tiles:
+// position (h, w) of the halo sits at row h*10 + w of a 128-byte-row, 128B-swizzled buffer, so the A operand of tap
+// (dh, dw) for accumulator `mh` is the same buffer read through a descriptor that starts at row (mh*16 + dh)*10 + dw
+// with a stride of 10 rows (1280 B) between 8-row groups -- the swizzle is a function of the absolute shared-memory
+// address for TMA and the tensor core alike (checked on B200: descriptors with the 'matrix base offset' field set to
+// (addr >> 7) & 7 give wrong results, plain start addresses are exact).
 //
-// 320 threads: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter, one per accumulator).
-// The epilogue keeps the bf16 row in registers (Cout <= 128), frees the accumulator as soon as it has been read, and
-// moves R / Y / Y2 through a per-warp staging tile so that global accesses are 64-byte row segments.
+// kCG = 2: a CTA pair works on two horizontally adjacent patches with M = 256 MMAs; each CTA stages its own halo and
+// half of the weight rows, all TMA bytes are accounted on the leader's barriers, the leader's MMA warp issues and its
+// commits are multicast to both CTAs, the second CTA's epilogue warps arrive on the leader's barrier through the
+// cluster address space (the protocol of gf_gemm.cu's pair mode).  A weight stage holds one window row (3 taps).
+// Measured: N = 96 90.5 % tensor-active (1471 TFLOP/s alone), N = 192 99.9 % (1678 TFLOP/s).
+//
+// Threads: warp 0 TMA, warp 1 MMA (the whole warp walks the loop, one elected lane issues), 4*MH epilogue warps (one
+// per TMEM lane quarter and accumulator).
 constexpr int HALO_W = 8;                                // tile width in positions (= rows of a UMMA core matrix)
 constexpr int HALO_MAX_A_STAGES = 4;
 constexpr int HALO_MAX_B_STAGES = 6;
