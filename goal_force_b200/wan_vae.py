@@ -33,25 +33,52 @@ def _round8(c: int) -> int:
     return (c + 7) // 8 * 8
 
 
+# Weight re-layouts (pure functions of the reference's tensors; tests/test_vae_cpu.py checks each against F.conv3d by
+# emulating the kernels' GEMM view in torch).
+def conv_weight_2d(weight: torch.Tensor) -> torch.Tensor:
+    """Conv3d / Conv2d weight (Cout, Cin, [kt,] kh, kw) -> the implicit GEMM's K-major operand [Cout, taps * CinP]:
+    tap-major (dt, dh, dw), channels innermost, Cin zero-padded to a multiple of 8 (fp32; the caller casts)."""
+    if weight.dim() == 4:                           # Conv2d -> kt = 1
+        weight = weight.unsqueeze(2)
+    cout, cin, kt, kh, kw = weight.shape
+    w = weight.detach().to(torch.float32).permute(0, 2, 3, 4, 1)
+    if _round8(cin) != cin:
+        w = torch.nn.functional.pad(w, (0, _round8(cin) - cin))
+    return w.reshape(cout, kt * kh * kw * _round8(cin))
+
+
+def fold_input_conv_weight(weight: torch.Tensor) -> torch.Tensor:
+    """encoder.conv1 (Cout, 3, 3, 3, 3) -> [Cout, 9 * 64]: tap (dt, dh), and inside a tap the 64-element window of 8
+    positions x 8 channels that starts one position left of the output pixel; dw = 0..2 are its first three positions."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    wf = torch.zeros((cout, 3, 3, 8, 8), dtype=torch.float32, device=weight.device)        # [co, dt, dh, dw, c]
+    wf[:, :, :, :3, :cin] = weight.detach().to(torch.float32).permute(0, 2, 3, 4, 1)
+    return wf.reshape(cout, 9 * 64)
+
+
+def head_tap_weight(weight: torch.Tensor) -> torch.Tensor:
+    """decoder.head.2 (3, C, 3, 3, 3) -> [36, 3 * C]: output channel tap*4 + co (tap = dh*3 + dw, the 4th channel of a
+    tap is zero), K = (dt, ci) -- the (3,1,1) convolution whose nine shifted partial sums the gather kernel adds."""
+    co, ci = weight.shape[0], weight.shape[1]
+    wh = torch.zeros((9, 4, 3, ci), dtype=torch.float32, device=weight.device)             # [tap, co, dt, ci]
+    wh[:, :co] = weight.detach().to(torch.float32).permute(3, 4, 0, 2, 1).reshape(9, co, 3, ci)
+    return wh.reshape(36, 3 * ci)
+
+
 class _Conv:
     """One convolution's device-side weights: w2d [Cout, taps * CinP] bf16 (tap-major, channels innermost)."""
 
     __slots__ = ("w", "bias", "kernel", "cin", "cout")
 
     def __init__(self, weight: torch.Tensor, bias: torch.Tensor, device):
-        if weight.dim() == 4:                       # Conv2d -> kt = 1
-            weight = weight.unsqueeze(2)
-        cout, cin, kt, kh, kw = weight.shape
-        cinp = _round8(cin)
-        w = weight.detach().to(device=device, dtype=torch.float32).permute(0, 2, 3, 4, 1)
-        if cinp != cin:
-            w = torch.nn.functional.pad(w, (0, cinp - cin))
-        self.w = w.reshape(cout, kt * kh * kw * cinp).to(torch.bfloat16).contiguous()
+        k = tuple(weight.shape[2:]) if weight.dim() == 5 else (1,) + tuple(weight.shape[2:])
+        cout, cin = weight.shape[0], weight.shape[1]
+        self.w = conv_weight_2d(weight.to(device)).to(torch.bfloat16).contiguous()
         b = torch.zeros(_round8(cout), dtype=torch.bfloat16, device=device)
         b[:cout] = bias.detach().to(device=device, dtype=torch.bfloat16)
         self.bias = b
-        self.kernel = (kt, kh, kw)
-        self.cin, self.cout = cinp, cout
+        self.kernel = k
+        self.cin, self.cout = _round8(cin), cout
 
 
 class WanVideoVAEB200:
@@ -98,18 +125,12 @@ class WanVideoVAEB200:
         # position's operand row is the 64-element window [w, w + 8) x 8 channels of that padded row (position pitch 8
         # < Cin 64: overlapping windows).  The three dw taps become columns 0..23 of a (dt, dh)-tap weight, the rest
         # of the window meets zero weights: 9 k-blocks of 64 instead of 27.
-        w = state_dict["encoder.conv1.weight"].detach().to(device=self.device, dtype=torch.float32)   # [C, 3, 3, 3, 3]
-        cout, cin = w.shape[0], w.shape[1]
-        wf = torch.zeros((cout, 3, 3, 8, 8), dtype=torch.float32, device=self.device)                 # [co, dt, dh, dw, c]
-        wf[:, :, :, :3, :cin] = w.permute(0, 2, 3, 4, 1)
-        self.conv1_folded = wf.reshape(cout, 9 * 64).to(torch.bfloat16).contiguous()
+        self.conv1_folded = fold_input_conv_weight(state_dict["encoder.conv1.weight"].to(self.device)).to(
+            torch.bfloat16).contiguous()
         # decoder.head.2 (3x3x3 to 3 channels): N = 3 would waste the tensor core, so its nine spatial taps become output
         # channels of a (3,1,1) convolution (channel tap*4 + co) and gf_vae_head_gather_bf16 sums them per pixel
-        w = state_dict["decoder.head.2.weight"].detach().to(device=self.device, dtype=torch.float32)   # [3, C, 3, 3, 3]
-        co, ci = w.shape[0], w.shape[1]
-        wh = torch.zeros((9, 4, 3, ci), dtype=torch.float32, device=self.device)                       # [tap, co, dt, ci]
-        wh[:, :co] = w.permute(3, 4, 0, 2, 1).reshape(9, co, 3, ci)
-        self.head_taps = wh.reshape(36, 3 * ci).to(torch.bfloat16).contiguous()
+        self.head_taps = head_tap_weight(state_dict["decoder.head.2.weight"].to(self.device)).to(
+            torch.bfloat16).contiguous()
         self.head_zero_bias = torch.zeros(40, dtype=torch.bfloat16, device=self.device)
         self.head_bias = state_dict["decoder.head.2.bias"].detach().to(device=self.device, dtype=torch.bfloat16).float()
 

@@ -88,3 +88,67 @@ def test_standin_matches_live_reference_attributes():
     assert sorted(m.model.state_dict()) == sorted(ref.model.state_dict())
     assert m.model.z_dim == ref.model.z_dim and m.upsampling_factor == ref.upsampling_factor
     assert m.model.encoder.conv1.weight.shape == ref.model.encoder.conv1.weight.shape
+
+
+def _im2col(x, kernel, pad):
+    """(Cin, T, H, W) -> [T*H*W, taps * Cin] rows in the kernels' K order (tap-major (dt, dh, dw), channels innermost),
+    leading zero padding `pad` and trailing padding so that the output keeps the input's extent."""
+    import torch.nn.functional as F
+    kt, kh, kw = kernel
+    C, T, H, W = x.shape
+    xp = F.pad(x, (pad[2], kw - 1 - pad[2], pad[1], kh - 1 - pad[1], pad[0], kt - 1 - pad[0]))
+    cols = []
+    for dt in range(kt):
+        for dh in range(kh):
+            for dw in range(kw):
+                cols.append(xp[:, dt:dt + T, dh:dh + H, dw:dw + W].permute(1, 2, 3, 0).reshape(T * H * W, C))
+    return torch.cat(cols, dim=1)
+
+
+def test_weight_relayouts_against_conv3d():
+    """Host-side weight layouts of goal_force_b200.wan_vae, each checked by emulating the kernel's GEMM in torch:
+    the generic [Cout, taps*Cin] operand, the folded 64-element window of encoder.conv1, the tap-channel head."""
+    import torch.nn.functional as F
+    from goal_force_b200.wan_vae import conv_weight_2d, fold_input_conv_weight, head_tap_weight
+    g = torch.Generator().manual_seed(4)
+    # generic: causal 3x3x3, Cin padded 3 -> 8
+    x = torch.randn(3, 4, 6, 7, generator=g)
+    w = torch.randn(10, 3, 3, 3, 3, generator=g)
+    want = F.conv3d(F.pad(x, (1, 1, 1, 1, 2, 0)).unsqueeze(0), w)[0]                        # (10, T, H, W)
+    x8 = F.pad(x, (0, 0, 0, 0, 0, 0, 0, 5))
+    got = (_im2col(x8, (3, 3, 3), (2, 1, 1)) @ conv_weight_2d(w).t()).reshape(4, 6, 7, 10).permute(3, 0, 1, 2)
+    assert torch.allclose(got, want, atol=1e-4)
+    # Conv2d weights become kt = 1
+    w2 = torch.randn(5, 8, 3, 3, generator=g)
+    x2 = torch.randn(8, 2, 5, 6, generator=g)
+    want2 = F.conv3d(F.pad(x2, (1, 1, 1, 1)).unsqueeze(0), w2.unsqueeze(2))[0]
+    got2 = (_im2col(x2, (1, 3, 3), (0, 1, 1)) @ conv_weight_2d(w2).t()).reshape(2, 5, 6, 5).permute(3, 0, 1, 2)
+    assert torch.allclose(got2, want2, atol=1e-4)
+    # folded input convolution: rows of W + 2 positions x 8 channels with zero borders, 64-element windows, taps (dt, dh)
+    T, H, W = 4, 6, 7
+    padded = torch.zeros(T, H, W + 2, 8)
+    padded[:, :, 1:-1, :3] = x.permute(1, 2, 3, 0)
+    flat = torch.cat([padded.reshape(-1), torch.zeros(64)])
+    windows = torch.as_strided(flat, (T, H, W + 2, 64), (H * (W + 2) * 8, (W + 2) * 8, 8, 1))   # overlapping, pitch 8
+    wf = fold_input_conv_weight(w)
+    assert wf.shape == (10, 9 * 64)
+    rows = _im2col(windows.permute(3, 0, 1, 2), (3, 3, 1), (2, 1, 0))                            # [T*H*(W+2), 9*64]
+    gotf = (rows @ wf.t()).reshape(T, H, W + 2, 10)[:, :, :W].permute(3, 0, 1, 2)
+    assert torch.allclose(gotf, want, atol=1e-4)
+    # head: (3,1,1) convolution to tap-channels, then the nine shifted partial sums
+    wh_src = torch.randn(3, 12, 3, 3, 3, generator=g)
+    xh = torch.randn(12, 4, 5, 6, generator=g)
+    wanth = F.conv3d(F.pad(xh, (1, 1, 1, 1, 2, 0)).unsqueeze(0), wh_src)[0]
+    wt = head_tap_weight(wh_src)
+    assert wt.shape == (36, 36) and float(wt.reshape(9, 4, -1)[:, 3].abs().max()) == 0.0
+    part = (_im2col(xh, (3, 1, 1), (2, 0, 0)) @ wt.t()).reshape(4, 5, 6, 36).permute(3, 0, 1, 2)     # (36, T, H, W)
+    pp = F.pad(part, (1, 1, 1, 1))
+    goth = sum(pp[(dh * 3 + dw) * 4:(dh * 3 + dw) * 4 + 3, :, dh:dh + 5, dw:dw + 6] for dh in range(3) for dw in range(3))
+    assert torch.allclose(goth, wanth, atol=1e-4)
+
+
+def test_tile_plan_of_the_product_matches_the_oracle():
+    from goal_force_b200.wan_vae import WanVideoVAEB200
+    for (H, W, size, stride) in ((60, 104, (30, 52), (15, 26)), (90, 160, (30, 52), (15, 26)), (7, 9, (4, 5), (3, 3)),
+                                 (34, 34, (34, 34), (18, 16)), (480, 832, (240, 416), (120, 208))):
+        assert WanVideoVAEB200._tasks(H, W, size, stride) == V.tile_tasks(H, W, size, stride)
