@@ -1,0 +1,12 @@
+import sys, torch
+sys.path.insert(0, "/root/repo")
+from goal_force_b200 import capi
+M, N, K = 4095, 5120, 13824
+a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
+b = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
+out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+for bn in (256, 224):
+    capi.gemm_tile_tuning(bn)
+    capi.gemm(a, w, b, out=out)
+torch.cuda.synchronize()
