@@ -347,3 +347,30 @@ def test_job_driver_callables_on_the_b200_vae(golden_dir):
     with torch.no_grad():
         want_y = V.encode(sd, clip, dim=dim)
     assert O.rel_l2(y[0, 4:].float().cpu(), want_y[0]) < 2e-2
+
+
+def test_single_frame_and_odd_sizes(golden_dir):
+    """T = 1 (an image: no temporal up / down-sampling happens, wan_video_vae.py:138-174), a 5-frame clip, and spatial
+    sizes that are not multiples of the kernels' tiles -- against the fp32 oracle, budget = the oracle's own bf16 run."""
+    from goal_force_b200.wan_vae import WanVideoVAEB200
+    g, sd = _golden(golden_dir)
+    dim = g["dim"]
+    vae = WanVideoVAEB200(sd, dim=dim)
+    gen = torch.Generator().manual_seed(21)
+    for (T, h, w) in ((1, 5, 7), (2, 3, 11), (1, 9, 4)):
+        z = torch.randn(1, 16, T, h, w, generator=gen)
+        with torch.no_grad():
+            want = V.decode(sd, z, dim=dim)
+        got = vae.decode(z.to(torch.bfloat16), "cuda").float().cpu()
+        assert got.shape == (1, 3, 4 * T - 3, 8 * h, 8 * w)
+        err = O.rel_l2(got, want.clamp(-1, 1))
+        budget = _bf16_oracle_err(lambda s_, x_, **kw: V.decode(s_, x_, **kw).clamp(-1, 1), sd, z, want.clamp(-1, 1), dim=dim)
+        assert err <= max(budget, 5e-3), (T, h, w, err, budget)
+        video = want.clamp(-1, 1)
+        with torch.no_grad():
+            want_e = V.encode(sd, video, dim=dim)
+        got_e = vae.encode(video.to(torch.bfloat16), "cuda").float().cpu()
+        assert got_e.shape == (1, 16, T, h, w)
+        err_e = O.rel_l2(got_e, want_e)
+        budget_e = _bf16_oracle_err(V.encode, sd, video, want_e, dim=dim)
+        assert err_e <= max(budget_e, 5e-3), (T, h, w, err_e, budget_e)
