@@ -69,6 +69,7 @@ class Job:
     index: int = 0
     control_video: torch.Tensor | None = None          # (F, H, W, 3) bf16, host
     result: torch.Tensor | None = None                 # final latents (1, 16, T, H/8, W/8)
+    video: torch.Tensor | None = None                  # decoded frames (1, 3, F, H, W) in [-1, 1] when a decoder is given
     info: dict = field(default_factory=dict)
 
 
@@ -113,7 +114,11 @@ class BatchDriver:
 
     def __init__(self, denoiser: GoalForceDenoiser, encode_control: Callable, conditioning: Callable,
                  parallel: ParallelContext | None = None, num_frames: int = 81, height: int = 480, width: int = 832,
-                 num_inference_steps: int = 50, cfg_scale: float = 5.0, sigma_shift: float = 5.0, device="cuda"):
+                 num_inference_steps: int = 50, cfg_scale: float = 5.0, sigma_shift: float = 5.0, device="cuda",
+                 decode: Callable | None = None):
+        """decode: optional final latents (1, 16, T, H/8, W/8) -> video (1, 3, F, H, W) in [-1, 1]; in the reference
+        this is `vae.decode` at the end of the pipeline call (wan_video_new.py:731-734), see `vae_decoder`."""
+        self.decode = decode
         self.denoiser, self.encode_control, self.conditioning = denoiser, encode_control, conditioning
         self.parallel = parallel
         self.dims = (num_frames, height, width)
@@ -142,6 +147,8 @@ class BatchDriver:
             job.result = self.denoiser(noise, cond["context_posi"], cond.get("context_nega"), y=cond.get("y"),
                                        control_latents=control, num_inference_steps=self.steps,
                                        cfg_scale=self.cfg_scale, sigma_shift=self.sigma_shift)
+            if self.decode is not None:
+                job.video = self.decode(job.result)
             job.info = {"row": job.index, "control_digest_channels": [bool(video[..., c].any()) for c in range(3)]}
             if on_done is not None:
                 on_done(job)
@@ -159,6 +166,24 @@ def vae_control_encoder(vae, tiled: bool = True, tile_size=(30, 52), tile_stride
         return vae.encode(v, vae.device, tiled=tiled, tile_size=tile_size, tile_stride=tile_stride)
 
     return encode
+
+
+def vae_decoder(vae, tiled: bool = True, tile_size=(30, 52), tile_stride=(15, 26), group=None):
+    """`decode` on the B200 VAE: the pipeline's last stage (src/goal_force/wan_video_new.py:731-734) with its tiling
+    defaults.  `group`: the replica group that denoised the video -- its ranks then share the tiles (bit-identical
+    result on every rank)."""
+
+    def decode(latents: torch.Tensor) -> torch.Tensor:
+        return vae.decode(latents, vae.device, tiled=tiled, tile_size=tile_size, tile_stride=tile_stride, group=group)
+
+    return decode
+
+
+def video_to_uint8(video: torch.Tensor) -> torch.Tensor:
+    """vae_output_to_video (diffsynth/utils/__init__.py:76-91) without the PIL step: (1, 3, F, H, W) in [-1, 1] ->
+    (F, H, W, 3) uint8, ((x + 1) * 127.5).clip(0, 255) truncated like the reference's `.to(torch.uint8)`."""
+    frames = video[0].permute(1, 2, 3, 0).float()
+    return ((frames + 1.0) * (255.0 / 2.0)).clip(0, 255).to(torch.uint8)
 
 
 def vae_image_condition(vae, image: torch.Tensor, num_frames: int, tiled: bool = True, tile_size=(30, 52),

@@ -155,3 +155,29 @@ def test_replica_groups_take_contiguous_shards_world2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     assert ret["idx"] == [[0, 1, 2], [3, 4]]
+
+
+def test_decode_stage_and_uint8_frames():
+    """The optional decode stage runs after every row's denoising (wan_video_new.py:731-734), and video_to_uint8 is the
+    reference's vae_output_to_video arithmetic (diffsynth/utils/__init__.py:76-91)."""
+    den = _StubDenoiser()
+    cond = lambda row: dict(context_posi=torch.zeros(1, 4, 8), context_nega=None, y=None)  # noqa: E731
+    seen = []
+
+    def decode(lat):
+        seen.append(tuple(lat.shape))
+        return torch.linspace(-1.2, 1.2, 3 * 5 * 4 * 6).reshape(1, 3, 5, 4, 6)
+
+    drv = J.BatchDriver(den, J.synthetic_control_encoder("cpu"), cond, num_frames=5, height=32, width=48,
+                        num_inference_steps=2, cfg_scale=1.0, device="cpu", decode=decode)
+    rows = [dict(projectile_force_magnitude=100.0, projectile_force_angle=5.0, projectile_coordx=10, projectile_coordy=12,
+                 projectile_mass=2.0, target_indirect_force_magnitude=-1.0, target_indirect_force_angle=0.0,
+                 target_coordx=30, target_coordy=20, target_mass=-1.0, width=48, height=32) for _ in range(2)]
+    out = drv.run(rows)
+    assert len(seen) == 2 and all(j.video is not None and j.video.shape == (1, 3, 5, 4, 6) for j in out)
+    frames = J.video_to_uint8(out[0].video)
+    assert frames.shape == (5, 4, 6, 3) and frames.dtype == torch.uint8
+    v = out[0].video[0].permute(1, 2, 3, 0)
+    want = ((v - (-1)) * (255 / (1 - (-1)))).clip(0, 255).to(dtype=torch.uint8)        # the reference's expression
+    assert torch.equal(frames, want)
+    assert int(frames.min()) == 0 and int(frames.max()) == 255
