@@ -265,9 +265,19 @@ def gen_vae():
         assert O.rel_l2(V.encode(sd, video, dim=dim), out["encode"]) < 1e-5
         assert O.rel_l2(V.tiled_decode(sd, z_big, (4, 5), (3, 3), dim=dim), out["tiled_decode"]) < 1e-5
         assert O.rel_l2(V.tiled_encode(sd, out["tiled_decode"], (32, 40), (24, 24), dim=dim), out["tiled_encode"]) < 1e-5
-    out = {k: (v.to(torch.float16) if isinstance(v, torch.Tensor) and k in ("decode", "tiled_decode") else v)
+        # the shipped width (dim 96: 96 / 192 / 384 channels) on a tiny clip, again from the reference's own chunk walk
+        sd96 = V.random_state_dict(dim=96, seed=7)
+        ref96 = vae.VideoVAE_(dim=96, z_dim=16).eval().requires_grad_(False)
+        ref96.load_state_dict(sd96, strict=True)
+        z96 = torch.randn(1, 16, 2, 3, 4, generator=g)
+        out["z96"], out["weight_seed96"] = z96, 7
+        out["decode96"] = ref96.decode(z96, wrap.scale)
+        out["encode96"] = ref96.encode(out["decode96"].clamp(-1, 1), wrap.scale)
+        assert O.rel_l2(V.decode(sd96, z96), out["decode96"]) < 1e-5
+        assert O.rel_l2(V.encode(sd96, out["decode96"].clamp(-1, 1)), out["encode96"]) < 1e-5
+    out = {k: (v.to(torch.float16) if isinstance(v, torch.Tensor) and k in ("decode", "tiled_decode", "decode96") else v)
            for k, v in out.items()}
-    for k in ("decode", "encode", "tiled_decode", "tiled_encode"):
+    for k in ("decode", "encode", "tiled_decode", "tiled_encode", "decode96", "encode96"):
         print("vae", k, tuple(out[k].shape))
     torch.save(out, GOLDEN / "vae.pt")
 

@@ -25,6 +25,16 @@ def test_oracle_matches_reference_vectors(golden_dir):
         assert O.rel_l2(V.tiled_encode(sd, video, (32, 40), (24, 24), dim=dim), g["tiled_encode"]) < 1e-4
 
 
+def test_oracle_matches_reference_vectors_at_the_shipped_width(golden_dir):
+    """dim 96 (96 / 192 / 384 channels, the Wan2.1 VAE's width): decode and encode of a tiny clip produced by the
+    reference's own VideoVAE_ (oracle/gen_golden.py::gen_vae)."""
+    g = torch.load(golden_dir / "vae.pt", weights_only=False)
+    sd = V.random_state_dict(dim=96, seed=g["weight_seed96"])
+    with torch.no_grad():
+        assert O.rel_l2(V.decode(sd, g["z96"]), g["decode96"].float()) < 1e-3           # stored as fp16
+        assert O.rel_l2(V.encode(sd, g["decode96"].float().clamp(-1, 1)), g["encode96"]) < 2e-3
+
+
 def test_shapes_and_causality(golden_dir):
     g, sd = _case(golden_dir)
     dim = g["dim"]

@@ -248,6 +248,24 @@ def test_decode_and_encode_against_reference_vectors(golden_dir):
     assert err <= max(budget, 4e-3), (err, budget)
 
 
+def test_shipped_width_against_reference_vectors(golden_dir):
+    """dim 96 against the vectors of the reference's own VideoVAE_ (tests/golden/vae.pt: decode96 / encode96)."""
+    from goal_force_b200.wan_vae import WanVideoVAEB200
+    g = torch.load(golden_dir / "vae.pt", weights_only=False)
+    sd = V.random_state_dict(dim=96, seed=g["weight_seed96"])
+    vae = WanVideoVAEB200(sd, dim=96)
+    want = g["decode96"].float()
+    got = vae._decode_clip(g["z96"][0].to(device="cuda", dtype=torch.bfloat16)).float().cpu().unsqueeze(0)
+    err, budget = O.rel_l2(got, want), _bf16_oracle_err(V.decode, sd, g["z96"], want)
+    print(f"vae decode96 vs reference vectors: ours {err:.3e}  oracle-bf16 {budget:.3e}")
+    assert err <= max(budget, 4e-3), (err, budget)
+    video = want.clamp(-1, 1)
+    got_e = vae._encode_clip(video[0].to(device="cuda", dtype=torch.bfloat16)).float().cpu().unsqueeze(0)
+    err_e, budget_e = O.rel_l2(got_e, g["encode96"]), _bf16_oracle_err(V.encode, sd, video, g["encode96"])
+    print(f"vae encode96 vs reference vectors: ours {err_e:.3e}  oracle-bf16 {budget_e:.3e}")
+    assert err_e <= max(budget_e, 4e-3), (err_e, budget_e)
+
+
 def test_tiled_paths_against_reference_vectors(golden_dir):
     from goal_force_b200.wan_vae import WanVideoVAEB200
     g, sd = _golden(golden_dir)
