@@ -56,6 +56,8 @@ def test_context_is_per_object_not_process_wide(lib):
     assert lib.gf_ctx_set_attention(a, 128, 4) == 0
     assert lib.gf_ctx_set_attention(a, 96, 0) == -1 and lib.gf_ctx_set_attention(a, 80, 3) == -1
     assert lib.gf_ctx_set_gemm_raster(b, 16) == 0 and lib.gf_ctx_set_gemm_raster(b, -2) == -1
+    assert lib.gf_ctx_set_gemm_tile(b, 224) == 0 and lib.gf_ctx_set_gemm_tile(b, 0) == 0 and lib.gf_ctx_set_gemm_tile(b, 192) == -1
+    assert lib.gf_ctx_set_conv(b, 2) == 0 and lib.gf_ctx_set_conv(b, 3) == -1
     e, h, m = ctypes.c_longlong(7), ctypes.c_longlong(7), ctypes.c_longlong(7)
     assert lib.gf_ctx_stats(a, ctypes.byref(e), ctypes.byref(h), ctypes.byref(m)) == 0
     assert (e.value, h.value, m.value) == (0, 0, 0)
