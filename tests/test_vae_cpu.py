@@ -162,3 +162,52 @@ def test_tile_plan_of_the_product_matches_the_oracle():
     for (H, W, size, stride) in ((60, 104, (30, 52), (15, 26)), (90, 160, (30, 52), (15, 26)), (7, 9, (4, 5), (3, 3)),
                                  (34, 34, (34, 34), (18, 16)), (480, 832, (240, 416), (120, 208))):
         assert WanVideoVAEB200._tasks(H, W, size, stride) == V.tile_tasks(H, W, size, stride)
+
+
+def _tiles_worker(rank, world, port, ret):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from goal_force_b200.wan_vae import WanVideoVAEB200
+        vae = object.__new__(WanVideoVAEB200)              # host logic only: no CUDA library, no weights
+        vae.device = torch.device("cpu")
+        tasks = WanVideoVAEB200._tasks(7, 9, (4, 5), (3, 3))
+        computed = []
+
+        def fn(task):                                      # a tile whose content identifies its task and its owner
+            computed.append(task)
+            h, h_, w, w_ = task
+            return torch.full((3, 2, min(h_, 7) - h, min(w_, 9) - w), float(8 * h + w), dtype=torch.bfloat16)   # bf16-exact tags
+
+        def shape_of(task):
+            h, h_, w, w_ = task
+            return (3, 2, min(h_, 7) - h, min(w_, 9) - w)
+
+        seen = [(task, float(tile.float().mean()), tuple(tile.shape))
+                for task, tile in vae._tiles(tasks, fn, shape_of, dist.group.WORLD)]
+        assert [s_[0] for s_ in seen] == tasks                                   # the reference's task order, on every rank
+        assert all(v == 8 * task[0] + task[2] and shp == shape_of(task) for task, v, shp in seen)
+        assert computed == [task for i, task in enumerate(tasks) if i % world == rank]   # round-robin ownership
+        single = [(task, float(tile.float().mean())) for task, tile in vae._tiles(tasks, fn, shape_of, None)]
+        assert [(a, b) for a, b, _ in seen] == single
+        if rank == 0:
+            ret["n"] = len(tasks)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_tile_sharding_over_a_process_group_world2():
+    """WanVideoVAEB200._tiles under gloo, world size 2: tiles are computed round-robin, broadcast from their owners and
+    yielded in the reference's task order on every rank (the GPU test checks the decoded result bit for bit)."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s_:
+        s_.bind(("127.0.0.1", 0))
+        port = s_.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_tiles_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret["n"] == 6
