@@ -289,14 +289,24 @@ def run_ours(args, emit):
     if not args.no_e2e:
         res_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
         bufs = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
+
+        def e2e_step():
             for k, v in host.items():
                 bufs[k].copy_(v, non_blocking=True)
             o = step(bufs)
             res_host.copy_(o, non_blocking=True)
             torch.cuda.current_stream().synchronize()
+
+        # Every copy into `bufs` bumps the tensors' versions, so each e2e step rebuilds the step-invariant caches
+        # (text embedding, 50 x cross-attention K|V, ControlNet tokens): that work stays inside the timed region.  What
+        # the untimed pass below removes is the ONE-TIME cost of the first such step: ~50 fresh cudaMalloc calls for
+        # the second generation of cache entries (each one drains the launch queue), 20-360 ms spread over K steps.
+        for _ in range(min(args.warmup, 1)):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
         e1.record()
         barrier()
         e2e = e0.elapsed_time(e1)
