@@ -1,5 +1,8 @@
+"""Two launches of the pair GEMM at M = 4095, N = 5120, K = 13824 (256- then 224-wide tiles) for an `ncu --set full`
+capture: profiles/r02_gemm_tile_ncu.csv."""
 import sys, torch
-sys.path.insert(0, "/root/repo")
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from goal_force_b200 import capi
 M, N, K = 4095, 5120, 13824
 a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
